@@ -1,0 +1,373 @@
+// vc_api.cu -- the C ABI (include/varycoef_b200.h): handle management and the per-evaluation
+// orchestration  build (K1) -> bordered Cholesky (K2) -> finalize (K3)  on CUDA streams.
+#include "vc_handle.cuh"
+#include <math.h>
+#include <string.h>
+#include <limits.h>
+#include <new>
+
+static thread_local std::string g_create_error;
+
+extern int vc_dist_n2ll(vc_handle* h, const double* theta, int32_t mu_mode, const double* mu_in,
+                        double* n2ll, double* mu_out, double* logdet, double* quad);
+extern void vc_dist_destroy(vc_handle* h);
+
+int vc_fail(vc_handle* h, int code, const std::string& msg) {
+  if (h) h->err = msg; else g_create_error = msg;
+  return code;
+}
+
+extern "C" int vc_abi_version(void) { return VC_ABI_VERSION; }
+
+extern "C" int vc_config_default(vc_config* cfg) {
+  if (!cfg) return VC_ERR_INVALID;
+  memset(cfg, 0, sizeof(*cfg));
+  cfg->cov_id = VC_COV_EXP;
+  cfg->dist_method = VC_DIST_EUCLIDEAN;
+  cfg->minkowski_p = 2.0;
+  cfg->taper_id = VC_TAPER_NONE;
+  cfg->taper_range = 0.0;
+  cfg->device = 0;
+  cfg->nb_outer = 0;
+  cfg->flags = 0;
+  return VC_OK;
+}
+
+static void upload_padded(double* dst, const double* src, int64_t n, int64_t n_pad, int cols,
+                          cudaStream_t st) {
+  // column-major n x cols -> n_pad x cols (tail rows stay zero)
+  VC_CUDA_TRY(cudaMemcpy2DAsync(dst, n_pad * sizeof(double), src, n * sizeof(double),
+                                n * sizeof(double), cols, cudaMemcpyHostToDevice, st));
+}
+
+int vc_validate_cfg(const vc_config* cfg, int64_t n, int d, int p, int q, std::string& why) {
+  if (n < 1) { why = "n must be >= 1"; return VC_ERR_INVALID; }
+  if (d < 1 || d > VC_MAXD) { why = "d (coordinate columns) must be in 1..8"; return VC_ERR_INVALID; }
+  if (p < 1 || p + 1 > VC_BORDER_ROWS) { why = "p must be in 1..127"; return VC_ERR_INVALID; }
+  if (q < 1 || q > VC_MAXQ) { why = "q must be in 1..32"; return VC_ERR_INVALID; }
+  if (cfg->cov_id < 0 || cfg->cov_id > VC_COV_WEND2) { why = "unknown cov_id"; return VC_ERR_INVALID; }
+  if (cfg->dist_method < 0 || cfg->dist_method > VC_DIST_MINKOWSKI) { why = "unknown dist_method"; return VC_ERR_INVALID; }
+  if (cfg->taper_id < 0 || cfg->taper_id > VC_TAPER_WEND2) { why = "unknown taper_id"; return VC_ERR_INVALID; }
+  if (cfg->taper_id != VC_TAPER_NONE && !(cfg->taper_range > 0.0)) { why = "taper_range must be > 0"; return VC_ERR_INVALID; }
+  if (cfg->dist_method == VC_DIST_MINKOWSKI && !(cfg->minkowski_p > 0.0)) { why = "minkowski_p must be > 0"; return VC_ERR_INVALID; }
+  if (cfg->nb_outer < 0 || cfg->nb_outer % VC_TILE != 0) { why = "nb_outer must be a multiple of 128"; return VC_ERR_INVALID; }
+  return VC_OK;
+}
+
+void vc_free_handle(vc_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->dist) vc_dist_destroy(h);
+  cudaFree(h->M.a); cudaFree(h->locs); cudaFree(h->x); cudaFree(h->w); cudaFree(h->y);
+  cudaFree(h->mu_in); cudaFree(h->results);
+  if (h->results_host) cudaFreeHost(h->results_host);
+  cudaFree(h->cw.linv); cudaFree(h->cw.logdet_part); cudaFree(h->cw.info);
+  cudaFree(h->fw.gram_part); cudaFree(h->fw.quad_part);
+  for (auto& e : h->ev) if (e) cudaEventDestroy(e);
+  if (h->cw.ev_panel) cudaEventDestroy(h->cw.ev_panel);
+  if (h->cw.ev_update) cudaEventDestroy(h->cw.ev_update);
+  if (h->cw.ev_col) cudaEventDestroy(h->cw.ev_col);
+  if (h->st_main) cudaStreamDestroy(h->st_main);
+  if (h->st_panel) cudaStreamDestroy(h->st_panel);
+  delete h;
+}
+
+static void ensure_result_slots(vc_handle* h, int m) {
+  if (m <= h->result_slots) return;
+  cudaFree(h->results); cudaFree(h->mu_in);
+  if (h->results_host) cudaFreeHost(h->results_host);
+  h->results = nullptr; h->mu_in = nullptr; h->results_host = nullptr; h->result_slots = 0;
+  VC_CUDA_TRY(cudaMalloc(&h->results, (size_t)m * VC_RES_STRIDE * sizeof(double)));
+  VC_CUDA_TRY(cudaMalloc(&h->mu_in, (size_t)m * 128 * sizeof(double)));
+  VC_CUDA_TRY(cudaMallocHost(&h->results_host, (size_t)m * VC_RES_STRIDE * sizeof(double)));
+  h->result_slots = m;
+}
+
+// shared by vc_create and vc_create_dist (which passes its own local matrix shape later)
+vc_handle* vc_alloc_common(const vc_config* cfg, int64_t n, int d, int p, int q, const double* locs,
+                           const double* X, const double* W, const double* y, bool alloc_matrix) {
+  vc_handle* h = new vc_handle();
+  h->cfg = *cfg;
+  h->n = n; h->d = d; h->p = p; h->q = q; h->device = cfg->device;
+  h->n_pad = (n + VC_TILE - 1) / VC_TILE * VC_TILE;
+  try {
+    VC_CUDA_TRY(cudaSetDevice(h->device));
+    int lo = 0, hi = 0;
+    VC_CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    VC_CUDA_TRY(cudaStreamCreateWithPriority(&h->st_main, cudaStreamNonBlocking, lo));
+    VC_CUDA_TRY(cudaStreamCreateWithPriority(&h->st_panel, cudaStreamNonBlocking, hi));
+    for (auto& e : h->ev) VC_CUDA_TRY(cudaEventCreate(&e));
+    VC_CUDA_TRY(cudaEventCreateWithFlags(&h->cw.ev_panel, cudaEventDisableTiming));
+    VC_CUDA_TRY(cudaEventCreateWithFlags(&h->cw.ev_update, cudaEventDisableTiming));
+    VC_CUDA_TRY(cudaEventCreateWithFlags(&h->cw.ev_col, cudaEventDisableTiming));
+    const int64_t np = h->n_pad;
+    VC_CUDA_TRY(cudaMalloc(&h->locs, np * d * sizeof(double)));
+    VC_CUDA_TRY(cudaMalloc(&h->x, np * p * sizeof(double)));
+    VC_CUDA_TRY(cudaMalloc(&h->w, np * q * sizeof(double)));
+    VC_CUDA_TRY(cudaMalloc(&h->y, np * sizeof(double)));
+    VC_CUDA_TRY(cudaMemsetAsync(h->locs, 0, np * d * sizeof(double), h->st_main));
+    VC_CUDA_TRY(cudaMemsetAsync(h->x, 0, np * p * sizeof(double), h->st_main));
+    VC_CUDA_TRY(cudaMemsetAsync(h->w, 0, np * q * sizeof(double), h->st_main));
+    VC_CUDA_TRY(cudaMemsetAsync(h->y, 0, np * sizeof(double), h->st_main));
+    upload_padded(h->locs, locs, n, np, d, h->st_main);
+    upload_padded(h->x, X, n, np, p, h->st_main);
+    upload_padded(h->w, W, n, np, q, h->st_main);
+    upload_padded(h->y, y, n, np, 1, h->st_main);
+    ensure_result_slots(h, 64);
+    h->M.n = n; h->M.n_pad = np; h->M.nt = (int)(np / VC_TILE);
+    h->M.lda = np + VC_BORDER_ROWS;
+    h->cw.nb_tiles = (cfg->nb_outer > 0 ? cfg->nb_outer : 512) / VC_TILE;
+    h->cw.lookahead = !(cfg->flags & VC_FLAG_NO_LOOKAHEAD);
+    h->cw.st_main = h->st_main; h->cw.st_panel = h->st_panel;
+    if (alloc_matrix) {
+      VC_CUDA_TRY(cudaMalloc(&h->M.a, (size_t)h->M.lda * np * sizeof(double)));
+      VC_CUDA_TRY(cudaMalloc(&h->cw.linv, (size_t)h->M.nt * VC_TILE * VC_TILE * sizeof(double)));
+      VC_CUDA_TRY(cudaMalloc(&h->cw.logdet_part, (size_t)h->M.nt * sizeof(double)));
+    }
+    VC_CUDA_TRY(cudaMalloc(&h->cw.info, sizeof(int)));
+    int blocks = (int)(n / 512);
+    if (blocks < 1) blocks = 1;
+    if (blocks > 148) blocks = 148;
+    h->fw.blocks = blocks;
+    const int m = p + 1;
+    VC_CUDA_TRY(cudaMalloc(&h->fw.gram_part, (size_t)blocks * m * (m + 1) * sizeof(double)));
+    VC_CUDA_TRY(cudaMalloc(&h->fw.quad_part, (size_t)blocks * 2 * sizeof(double)));
+    vc_build_init();
+    vc_chol_init();
+    VC_CUDA_TRY(cudaStreamSynchronize(h->st_main));
+  } catch (const VcError& e) {
+    g_create_error = e.msg;
+    vc_free_handle(h);
+    throw;
+  }
+  return h;
+}
+
+extern "C" int vc_create(vc_handle** out, const vc_config* cfg_in, int64_t n, int32_t d, int32_t p,
+                         int32_t q, const double* locs, const double* X, const double* W,
+                         const double* y) {
+  if (!out) return VC_ERR_INVALID;
+  *out = nullptr;
+  vc_config cfg;
+  if (cfg_in) cfg = *cfg_in; else vc_config_default(&cfg);
+  if (!locs || !X || !W || !y) return vc_fail(nullptr, VC_ERR_INVALID, "NULL input pointer");
+  std::string why;
+  if (vc_validate_cfg(&cfg, n, d, p, q, why) != VC_OK) return vc_fail(nullptr, VC_ERR_INVALID, why);
+  try {
+    *out = vc_alloc_common(&cfg, n, d, p, q, locs, X, W, y, true);
+  } catch (const VcError& e) {
+    return vc_fail(nullptr, e.code, e.msg);
+  } catch (const std::bad_alloc&) {
+    return vc_fail(nullptr, VC_ERR_OOM, "host allocation failed");
+  }
+  return VC_OK;
+}
+
+extern "C" void vc_destroy(vc_handle* h) { vc_free_handle(h); }
+
+extern "C" int vc_set_data(vc_handle* h, const double* locs, const double* X, const double* W,
+                           const double* y) {
+  if (!h) return VC_ERR_INVALID;
+  try {
+    VC_CUDA_TRY(cudaSetDevice(h->device));
+    if (locs) upload_padded(h->locs, locs, h->n, h->n_pad, h->d, h->st_main);
+    if (X) upload_padded(h->x, X, h->n, h->n_pad, h->p, h->st_main);
+    if (W) upload_padded(h->w, W, h->n, h->n_pad, h->q, h->st_main);
+    if (y) upload_padded(h->y, y, h->n, h->n_pad, 1, h->st_main);
+    h->factor_valid = false;
+  } catch (const VcError& e) {
+    return vc_fail(h, e.code, e.msg);
+  }
+  return VC_OK;
+}
+
+// theta -> kernel parameter block; VC_ERR_INVALID when a value cannot define a covariance
+int vc_make_theta(const vc_handle* h, const double* theta, VcTheta* t) {
+  memset(t, 0, sizeof(*t));
+  t->q = h->q;
+  t->cov_id = h->cfg.cov_id;
+  t->taper_id = h->cfg.taper_id;
+  t->dist_method = h->cfg.dist_method;
+  t->mink_p = h->cfg.minkowski_p;
+  t->inv_delta = h->cfg.taper_id != VC_TAPER_NONE ? 1.0 / h->cfg.taper_range : 0.0;
+  for (int k = 0; k < h->q; ++k) {
+    const double rho = theta[2 * k], s2 = theta[2 * k + 1];
+    if (!(rho > 0.0) || !isfinite(rho) || !isfinite(s2)) return VC_ERR_INVALID;
+    t->inv_range[k] = 1.0 / rho;
+    t->sill[k] = s2;
+  }
+  t->tau2 = theta[2 * h->q];
+  if (!isfinite(t->tau2)) return VC_ERR_INVALID;
+  return VC_OK;
+}
+
+// enqueue one evaluation on the handle's streams; result record `slot`
+static void enqueue_eval(vc_handle* h, const VcTheta& th, int mu_mode, int slot, bool timed) {
+  cudaStream_t st = h->st_main;
+  if (timed) VC_CUDA_TRY(cudaEventRecord(h->ev[0], st));
+  vc_launch_build(h->M, th, h->d, h->locs, h->w, st, &h->launches);
+  vc_launch_border(h->M, h->p, h->x, h->y, st, &h->launches);
+  if (timed) VC_CUDA_TRY(cudaEventRecord(h->ev[1], st));
+  vc_chol_factor(h->M, h->cw, &h->launches);
+  if (timed) VC_CUDA_TRY(cudaEventRecord(h->ev[2], st));
+  vc_launch_finalize(h->M, h->p, mu_mode, h->mu_in + (size_t)slot * 128, h->cw.logdet_part,
+                     h->cw.info, h->fw, h->results + (size_t)slot * VC_RES_STRIDE, st, &h->launches);
+  if (timed) VC_CUDA_TRY(cudaEventRecord(h->ev[3], st));
+}
+
+extern "C" int vc_n2ll_batch(vc_handle* h, int32_t m, const double* thetas, int32_t mu_mode,
+                             const double* mus_in, double* out_n2ll, double* out_mu,
+                             int32_t* out_status) {
+  if (!h) return VC_ERR_INVALID;
+  if (m < 1 || !thetas || !out_n2ll) return vc_fail(h, VC_ERR_INVALID, "bad batch arguments");
+  if (mu_mode != VC_MU_GLS && mu_mode != VC_MU_FIXED) return vc_fail(h, VC_ERR_INVALID, "unknown mu_mode");
+  if (mu_mode == VC_MU_FIXED && !mus_in) return vc_fail(h, VC_ERR_INVALID, "mu_mode FIXED needs mu");
+  if (h->dist) {
+    int first = VC_OK;
+    for (int e = 0; e < m; ++e) {
+      int s = vc_dist_n2ll(h, thetas + (size_t)e * (2 * h->q + 1), mu_mode,
+                           mus_in ? mus_in + (size_t)e * h->p : nullptr, out_n2ll + e,
+                           out_mu ? out_mu + (size_t)e * h->p : nullptr, nullptr, nullptr);
+      if (out_status) out_status[e] = s;
+      if (s != VC_OK && first == VC_OK) first = s;
+    }
+    return first;
+  }
+  const int nth = 2 * h->q + 1;
+  int first = VC_OK;
+  try {
+    VC_CUDA_TRY(cudaSetDevice(h->device));
+    ensure_result_slots(h, m);
+    std::vector<int> status(m, VC_OK);
+    if (mu_mode == VC_MU_FIXED)
+      VC_CUDA_TRY(cudaMemcpy2DAsync(h->mu_in, 128 * sizeof(double), mus_in, h->p * sizeof(double),
+                                    h->p * sizeof(double), m, cudaMemcpyHostToDevice, h->st_main));
+    for (int e = 0; e < m; ++e) {
+      VcTheta th;
+      if (vc_make_theta(h, thetas + (size_t)e * nth, &th) != VC_OK) {
+        status[e] = VC_ERR_INVALID;
+        continue;
+      }
+      enqueue_eval(h, th, mu_mode, e, e == m - 1);
+    }
+    VC_CUDA_TRY(cudaMemcpyAsync(h->results_host, h->results, (size_t)m * VC_RES_STRIDE * sizeof(double),
+                                cudaMemcpyDeviceToHost, h->st_main));
+    VC_CUDA_TRY(cudaStreamSynchronize(h->st_main));
+    VC_CUDA_TRY(cudaGetLastError());
+    for (int e = 0; e < m; ++e) {
+      const double* r = h->results_host + (size_t)e * VC_RES_STRIDE;
+      if (status[e] == VC_OK) {
+        const int info = (int)r[VC_RES_INFO];
+        if (info != 0) { status[e] = VC_ERR_NOT_PD; h->last_info = info; }
+        out_n2ll[e] = r[VC_RES_N2LL];
+        if (out_mu) for (int i = 0; i < h->p; ++i) out_mu[(size_t)e * h->p + i] = r[VC_RES_MU + i];
+      } else {
+        out_n2ll[e] = NAN;
+        if (out_mu) for (int i = 0; i < h->p; ++i) out_mu[(size_t)e * h->p + i] = NAN;
+      }
+      if (out_status) out_status[e] = status[e];
+      if (status[e] != VC_OK && first == VC_OK) first = status[e];
+    }
+    if (status[m - 1] == VC_OK || status[m - 1] == VC_ERR_NOT_PD) {
+      float b = 0, c = 0, f = 0;
+      cudaEventElapsedTime(&b, h->ev[0], h->ev[1]);
+      cudaEventElapsedTime(&c, h->ev[1], h->ev[2]);
+      cudaEventElapsedTime(&f, h->ev[2], h->ev[3]);
+      h->last_timing = {b, c, f, b + c + f};
+    }
+    h->factor_valid = (status[m - 1] == VC_OK);
+    if (first == VC_ERR_NOT_PD) {
+      char buf[128];
+      snprintf(buf, sizeof(buf), "the leading minor of order %d is not positive", h->last_info);
+      h->err = buf;
+    } else if (first == VC_ERR_INVALID) {
+      h->err = "theta does not define a covariance (range <= 0 or non-finite value)";
+    }
+  } catch (const VcError& e) {
+    return vc_fail(h, e.code, e.msg);
+  }
+  return first;
+}
+
+extern "C" int vc_n2ll(vc_handle* h, const double* theta, int32_t mu_mode, const double* mu_in,
+                       double* n2ll, double* mu_out, double* logdet, double* quad) {
+  if (!h || !theta || !n2ll) return VC_ERR_INVALID;
+  if (h->dist) return vc_dist_n2ll(h, theta, mu_mode, mu_in, n2ll, mu_out, logdet, quad);
+  int32_t status = VC_OK;
+  h->last_info = 0;
+  int rc = vc_n2ll_batch(h, 1, theta, mu_mode, mu_in, n2ll, mu_out, &status);
+  if (rc == VC_OK || rc == VC_ERR_NOT_PD) {
+    if (logdet) *logdet = h->results_host[VC_RES_LOGDET];
+    if (quad) *quad = h->results_host[VC_RES_QUAD];
+  }
+  return rc;
+}
+
+extern "C" int vc_sigma(vc_handle* h, const double* theta, double* out) {
+  if (!h || !theta || !out) return VC_ERR_INVALID;
+  if (h->dist) return vc_fail(h, VC_ERR_INVALID, "vc_sigma is not available on a distributed handle");
+  VcTheta th;
+  if (vc_make_theta(h, theta, &th) != VC_OK) return vc_fail(h, VC_ERR_INVALID, "invalid theta");
+  double* dev = nullptr;
+  try {
+    VC_CUDA_TRY(cudaSetDevice(h->device));
+    VC_CUDA_TRY(cudaMalloc(&dev, (size_t)h->n * h->n * sizeof(double)));
+    vc_launch_sigma_full(dev, h->n, h->n_pad, th, h->d, h->locs, h->w, h->st_main, &h->launches);
+    VC_CUDA_TRY(cudaMemcpyAsync(out, dev, (size_t)h->n * h->n * sizeof(double), cudaMemcpyDeviceToHost, h->st_main));
+    VC_CUDA_TRY(cudaStreamSynchronize(h->st_main));
+    cudaFree(dev);
+  } catch (const VcError& e) {
+    cudaFree(dev);
+    return vc_fail(h, e.code, e.msg);
+  }
+  return VC_OK;
+}
+
+extern "C" int vc_get_chol(vc_handle* h, double* R_out) {
+  if (!h || !R_out) return VC_ERR_INVALID;
+  if (h->dist) return vc_fail(h, VC_ERR_INVALID, "vc_get_chol is not available on a distributed handle");
+  if (!h->factor_valid) return vc_fail(h, VC_ERR_INVALID, "no valid factor: call vc_n2ll first");
+  double* dev = nullptr;
+  try {
+    VC_CUDA_TRY(cudaSetDevice(h->device));
+    VC_CUDA_TRY(cudaMalloc(&dev, (size_t)h->n * h->n * sizeof(double)));
+    vc_launch_extract_chol(h->M, dev, h->st_main, &h->launches);
+    VC_CUDA_TRY(cudaMemcpyAsync(R_out, dev, (size_t)h->n * h->n * sizeof(double), cudaMemcpyDeviceToHost, h->st_main));
+    VC_CUDA_TRY(cudaStreamSynchronize(h->st_main));
+    cudaFree(dev);
+  } catch (const VcError& e) {
+    cudaFree(dev);
+    return vc_fail(h, e.code, e.msg);
+  }
+  return VC_OK;
+}
+
+extern "C" int vc_get_whitened(vc_handle* h, double* Z_out) {
+  if (!h || !Z_out) return VC_ERR_INVALID;
+  if (h->dist) return vc_fail(h, VC_ERR_INVALID, "vc_get_whitened is not available on a distributed handle");
+  if (!h->factor_valid) return vc_fail(h, VC_ERR_INVALID, "no valid factor: call vc_n2ll first");
+  double* dev = nullptr;
+  try {
+    VC_CUDA_TRY(cudaSetDevice(h->device));
+    const size_t bytes = (size_t)h->n * (h->p + 1) * sizeof(double);
+    VC_CUDA_TRY(cudaMalloc(&dev, bytes));
+    vc_launch_gather_whitened(h->M, h->p, dev, h->st_main, &h->launches);
+    VC_CUDA_TRY(cudaMemcpyAsync(Z_out, dev, bytes, cudaMemcpyDeviceToHost, h->st_main));
+    VC_CUDA_TRY(cudaStreamSynchronize(h->st_main));
+    cudaFree(dev);
+  } catch (const VcError& e) {
+    cudaFree(dev);
+    return vc_fail(h, e.code, e.msg);
+  }
+  return VC_OK;
+}
+
+extern "C" int vc_timings(vc_handle* h, vc_timing* out) {
+  if (!h || !out) return VC_ERR_INVALID;
+  *out = h->last_timing;
+  return VC_OK;
+}
+extern "C" int vc_last_info(vc_handle* h) { return h ? h->last_info : 0; }
+extern "C" const char* vc_last_error(vc_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+extern "C" int64_t vc_padded_n(vc_handle* h) { return h ? h->n_pad : 0; }
+extern "C" int64_t vc_launch_count(vc_handle* h) { return h ? h->launches : 0; }

@@ -1,0 +1,222 @@
+// vc_build.cu -- K1: fused pairwise-distance + covariance build of Sigma_y (lower tiles).
+//
+// Replaces, in one write-only pass over HBM:
+//   own_dist            reference R-pkg/R/utils.R:508-543   (distance matrix, never materialised)
+//   cov.func closure    R-pkg/R/SVC_mle.R:58-61 + R-pkg/R/utils.R:2-29 (spam::cov.*)
+//   outer.W (x taper)   R-pkg/R/SVC_mle.R:65-72, get_taper R-pkg/R/utils.R:545-552
+//   Sigma_y             R-pkg/R/utils.R:171-233 (sum_k cov_k o W_k W_k^T + tau^2 I)
+//
+// One CTA = one 128x128 tile (I >= J).  Thread t owns rows 2*(t&63), +1 (one 16-byte store per
+// column, 512 contiguous bytes per warp) and the 32 columns (t>>6)*32.. of the tile.  Column
+// operands (coordinates, W_jk) are broadcast from shared memory; row operands stay in registers
+// when d <= 3 and q <= 8.  Padded rows/cols (index >= n) get W = 0 and a unit diagonal so the
+// padded matrix factors to [L 0; 0 I].
+#include "vc_common.cuh"
+#include "vc_math.cuh"
+
+namespace {
+
+constexpr int TILE = VC_TILE;
+constexpr int BUILD_THREADS = 256;
+constexpr int RD = 3;   // register-resident coordinate columns
+constexpr int RQ = 8;   // register-resident SVCs
+
+__constant__ double c_exp2_tab[VC_EXP_TABLE_SIZE];
+
+struct BuildArgs {
+  double* out;
+  int64_t ld;
+  int64_t n, n_pad;
+  int nt;
+  int d;
+  const double* locs;   // n_pad x d
+  const double* w;      // n_pad x q
+  VcTheta th;
+};
+
+// shared layout: tab[64] | colX[d][128] | colW[q][128] | rowX[d][128] | rowA[q][128]
+template <int COV, bool REG, bool FULL>
+__global__ void __launch_bounds__(BUILD_THREADS) k_build(BuildArgs p) {
+  extern __shared__ __align__(16) double sm[];
+  const int d = p.d, q = p.th.q;
+  double* tab = sm;
+  double* colX = tab + VC_EXP_TABLE_SIZE;
+  double* colW = colX + d * TILE;
+  double* rowX = colW + q * TILE;
+  double* rowA = rowX + d * TILE;
+
+  int I, J;
+  if (FULL) {
+    I = blockIdx.x % p.nt;
+    J = blockIdx.x / p.nt;
+  } else {
+    // lower-triangular tile enumeration: id = I (I + 1) / 2 + J
+    const int id = blockIdx.x;
+    I = (int)((sqrt(8.0 * id + 1.0) - 1.0) * 0.5);
+    while ((I + 1) * (I + 2) / 2 <= id) ++I;
+    while (I * (I + 1) / 2 > id) --I;
+    J = id - I * (I + 1) / 2;
+  }
+  const int tid = threadIdx.x;
+  if (tid < VC_EXP_TABLE_SIZE) tab[tid] = c_exp2_tab[tid];
+  for (int idx = tid; idx < d * TILE; idx += BUILD_THREADS) {
+    const int c = idx / TILE, r = idx % TILE;
+    colX[idx] = p.locs[(int64_t)c * p.n_pad + (int64_t)J * TILE + r];
+    rowX[idx] = p.locs[(int64_t)c * p.n_pad + (int64_t)I * TILE + r];
+  }
+  for (int idx = tid; idx < q * TILE; idx += BUILD_THREADS) {
+    const int k = idx / TILE, r = idx % TILE;
+    colW[idx] = p.w[(int64_t)k * p.n_pad + (int64_t)J * TILE + r];
+    rowA[idx] = p.w[(int64_t)k * p.n_pad + (int64_t)I * TILE + r] * p.th.sill[k];
+  }
+  __syncthreads();
+
+  const int rg = tid & 63, cg = tid >> 6;
+  const int r0 = 2 * rg;
+  const int64_t gi0 = (int64_t)I * TILE + r0;
+  const int method = p.th.dist_method;
+  const double mink = p.th.mink_p;
+
+  double xi0[RD], xi1[RD], ai0[RQ], ai1[RQ], ir[RQ];
+  if (REG) {
+#pragma unroll
+    for (int c = 0; c < RD; ++c)
+      if (c < d) { xi0[c] = rowX[c * TILE + r0]; xi1[c] = rowX[c * TILE + r0 + 1]; }
+#pragma unroll
+    for (int k = 0; k < RQ; ++k)
+      if (k < q) { ai0[k] = rowA[k * TILE + r0]; ai1[k] = rowA[k * TILE + r0 + 1]; ir[k] = p.th.inv_range[k]; }
+  }
+
+  for (int cc = 0; cc < 32; ++cc) {
+    const int j = cg * 32 + cc;
+    const int64_t gj = (int64_t)J * TILE + j;
+    double s0 = 0.0, s1 = 0.0;
+    if (REG) {
+#pragma unroll
+      for (int c = 0; c < RD; ++c)
+        if (c < d) {
+          const double xj = colX[c * TILE + j];
+          if (method == VC_DIST_EUCLIDEAN) {
+            const double d0 = xi0[c] - xj, d1 = xi1[c] - xj;
+            s0 = fma(d0, d0, s0);
+            s1 = fma(d1, d1, s1);
+          } else {
+            s0 = vc_dist_accum(method, s0, xi0[c] - xj, mink);
+            s1 = vc_dist_accum(method, s1, xi1[c] - xj, mink);
+          }
+        }
+    } else {
+      for (int c = 0; c < d; ++c) {
+        const double xj = colX[c * TILE + j];
+        s0 = vc_dist_accum(method, s0, rowX[c * TILE + r0] - xj, mink);
+        s1 = vc_dist_accum(method, s1, rowX[c * TILE + r0 + 1] - xj, mink);
+      }
+    }
+    double h0, h1;
+    if (method == VC_DIST_EUCLIDEAN) { h0 = sqrt(s0); h1 = sqrt(s1); }
+    else { h0 = vc_dist_finish(method, s0, mink); h1 = vc_dist_finish(method, s1, mink); }
+
+    double v0 = 0.0, v1 = 0.0;
+    if (REG) {
+#pragma unroll
+      for (int k = 0; k < RQ; ++k)
+        if (k < q) {
+          const double wj = colW[k * TILE + j];
+          v0 = fma(ai0[k] * wj, vc_cov_shape<COV>(h0 * ir[k], tab), v0);
+          v1 = fma(ai1[k] * wj, vc_cov_shape<COV>(h1 * ir[k], tab), v1);
+        }
+    } else {
+      for (int k = 0; k < q; ++k) {
+        const double wj = colW[k * TILE + j];
+        const double irk = p.th.inv_range[k];
+        v0 = fma(rowA[k * TILE + r0] * wj, vc_cov_shape<COV>(h0 * irk, tab), v0);
+        v1 = fma(rowA[k * TILE + r0 + 1] * wj, vc_cov_shape<COV>(h1 * irk, tab), v1);
+      }
+    }
+    if (p.th.taper_id != VC_TAPER_NONE) {
+      v0 *= vc_taper(p.th.taper_id, h0, p.th.inv_delta);
+      v1 *= vc_taper(p.th.taper_id, h1, p.th.inv_delta);
+    }
+    if (gi0 == gj) v0 += (gj < p.n) ? p.th.tau2 : 1.0;
+    if (gi0 + 1 == gj) v1 += (gj < p.n) ? p.th.tau2 : 1.0;
+    if (FULL) {
+      if (gj < p.n) {
+        if (gi0 < p.n) p.out[gi0 + gj * p.ld] = v0;
+        if (gi0 + 1 < p.n) p.out[gi0 + 1 + gj * p.ld] = v1;
+      }
+    } else {
+      *reinterpret_cast<double2*>(p.out + gi0 + gj * p.ld) = make_double2(v0, v1);
+    }
+  }
+}
+
+template <bool FULL>
+void launch_build_t(const BuildArgs& a, cudaStream_t st) {
+  const int d = a.d, q = a.th.q;
+  const bool reg = (d <= RD && q <= RQ);
+  const size_t smem = (VC_EXP_TABLE_SIZE + 2 * (size_t)(d + q) * TILE) * sizeof(double);
+  const unsigned grid = FULL ? (unsigned)a.nt * a.nt : (unsigned)((int64_t)a.nt * (a.nt + 1) / 2);
+#define VC_BUILD_CASE(C)                                                               \
+  case C:                                                                              \
+    if (reg) k_build<C, true, FULL><<<grid, BUILD_THREADS, smem, st>>>(a);             \
+    else k_build<C, false, FULL><<<grid, BUILD_THREADS, smem, st>>>(a);                \
+    break;
+  switch (a.th.cov_id) {
+    VC_BUILD_CASE(0) VC_BUILD_CASE(1) VC_BUILD_CASE(2) VC_BUILD_CASE(3) VC_BUILD_CASE(4)
+    default:
+      if (reg) k_build<5, true, FULL><<<grid, BUILD_THREADS, smem, st>>>(a);
+      else k_build<5, false, FULL><<<grid, BUILD_THREADS, smem, st>>>(a);
+  }
+#undef VC_BUILD_CASE
+}
+
+// border rows: A[n_pad + c, j] = X[j, c] (c < p), y[j] (c == p), 0 otherwise
+__global__ void k_border(double* a, int64_t lda, int64_t n_pad, int p, const double* __restrict__ x,
+                         const double* __restrict__ y) {
+  const int64_t j = (int64_t)blockIdx.x * 2 + (threadIdx.x >> 7);
+  const int c = threadIdx.x & 127;
+  if (j >= n_pad) return;
+  double v = 0.0;
+  if (c < p) v = x[(int64_t)c * n_pad + j];
+  else if (c == p) v = y[j];
+  a[n_pad + c + j * lda] = v;
+}
+
+}  // namespace
+
+void vc_build_init() {
+  static bool done_dev[64] = {false};
+  int dev = 0;
+  VC_CUDA_TRY(cudaGetDevice(&dev));
+  bool& done = done_dev[dev & 63];
+  if (done) return;
+  double tab[VC_EXP_TABLE_SIZE];
+  vc_fill_exp2_table(tab);
+  VC_CUDA_TRY(cudaMemcpyToSymbol(c_exp2_tab, tab, sizeof(tab)));
+  done = true;
+}
+
+void vc_launch_build(const VcMatrix& M, const VcTheta& th, int d, const double* locs_pad,
+                     const double* w_pad, cudaStream_t st, int64_t* launches) {
+  BuildArgs a{};
+  a.out = M.a; a.ld = M.lda; a.n = M.n; a.n_pad = M.n_pad; a.nt = M.nt; a.d = d;
+  a.locs = locs_pad; a.w = w_pad; a.th = th;
+  launch_build_t<false>(a, st);
+  ++*launches;
+}
+
+void vc_launch_sigma_full(double* out, int64_t n, int64_t n_pad, const VcTheta& th, int d,
+                          const double* locs_pad, const double* w_pad, cudaStream_t st,
+                          int64_t* launches) {
+  BuildArgs a{};
+  a.out = out; a.ld = n; a.n = n; a.n_pad = n_pad; a.nt = (int)(n_pad / TILE); a.d = d;
+  a.locs = locs_pad; a.w = w_pad; a.th = th;
+  launch_build_t<true>(a, st);
+  ++*launches;
+}
+
+void vc_launch_border(const VcMatrix& M, int p, const double* x_pad, const double* y_pad,
+                      cudaStream_t st, int64_t* launches) {
+  k_border<<<(unsigned)((M.n_pad + 1) / 2), 256, 0, st>>>(M.a, M.lda, M.n_pad, p, x_pad, y_pad);
+  ++*launches;
+}

@@ -1,0 +1,98 @@
+// vc_common.cuh -- shared definitions of the sm_100a likelihood library.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/varycoef_b200.h"
+
+#define VC_TILE 128            // tile edge of every kernel (rows/cols of Sigma are padded to it)
+#define VC_MAXQ 32             // SVCs per model supported by the by-value kernel parameter block
+#define VC_MAXD 8              // coordinate columns supported
+#define VC_BORDER_ROWS 128     // one extra row tile below Sigma holds [X y]^T (p + 1 <= 128)
+
+// covariance parameters of one evaluation, passed to kernels by value (no H2D copy on the path)
+struct VcTheta {
+  int q;
+  int cov_id;
+  int taper_id;
+  int dist_method;
+  double mink_p;
+  double inv_delta;            // 1 / taper range
+  double tau2;                 // nugget variance
+  double inv_range[VC_MAXQ];   // 1 / rho_k
+  double sill[VC_MAXQ];        // sigma_k^2
+};
+
+// layout of the per-evaluation result record in device memory (doubles)
+#define VC_RES_N2LL 0
+#define VC_RES_LOGDET 1
+#define VC_RES_QUAD 2
+#define VC_RES_INFO 3
+#define VC_RES_MU 4            // p doubles follow
+#define VC_RES_STRIDE (4 + 128)
+
+#define VC_CUDA_TRY(expr)                                                              \
+  do {                                                                                 \
+    cudaError_t _e = (expr);                                                           \
+    if (_e != cudaSuccess) {                                                           \
+      char _b[512];                                                                    \
+      snprintf(_b, sizeof(_b), "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+               __FILE__, __LINE__);                                                    \
+      throw VcError(_e == cudaErrorMemoryAllocation ? VC_ERR_OOM : VC_ERR_CUDA, _b);   \
+    }                                                                                  \
+  } while (0)
+
+struct VcError {
+  int code;
+  std::string msg;
+  VcError(int c, const std::string& m) : code(c), msg(m) {}
+};
+
+// ---- launchers implemented in the .cu files ------------------------------------------------
+struct VcMatrix {        // bordered, padded, column-major Sigma / factor in HBM
+  double* a;             // (n_pad + VC_BORDER_ROWS) x n_pad
+  int64_t lda;           // n_pad + VC_BORDER_ROWS
+  int64_t n;             // real order
+  int64_t n_pad;         // multiple of VC_TILE
+  int nt;                // n_pad / VC_TILE  (column tiles)
+};
+
+// vc_build.cu
+void vc_launch_build(const VcMatrix& M, const VcTheta& th, int d, const double* locs_pad,
+                     const double* w_pad, cudaStream_t st, int64_t* launches);
+void vc_launch_border(const VcMatrix& M, int p, const double* x_pad, const double* y_pad,
+                      cudaStream_t st, int64_t* launches);
+void vc_launch_sigma_full(double* out, int64_t n, int64_t n_pad, const VcTheta& th, int d,
+                          const double* locs_pad, const double* w_pad, cudaStream_t st,
+                          int64_t* launches);
+void vc_build_init();
+
+// vc_chol.cu
+struct VcCholWork {
+  double* linv;          // nt x (128 x 128): inverse of every diagonal factor tile
+  double* logdet_part;   // nt partial sums of log L_jj
+  int* info;             // first failing leading minor (INT_MAX if none)
+  int nb_tiles;          // outer block in tiles (nb_outer / 128)
+  bool lookahead;
+  cudaStream_t st_main, st_panel;
+  cudaEvent_t ev_panel, ev_update, ev_col;
+};
+void vc_chol_init();
+void vc_chol_factor(const VcMatrix& M, VcCholWork& w, int64_t* launches);
+
+// vc_finalize.cu
+struct VcFinalWork {
+  double* gram_part;     // blocks x npairs x 2 (hi, lo)
+  double* quad_part;     // blocks x 2
+  int blocks;
+};
+void vc_launch_finalize(const VcMatrix& M, int p, int mu_mode, const double* mu_in_dev,
+                        const double* logdet_part, const int* info, VcFinalWork& fw,
+                        double* result_dev, cudaStream_t st, int64_t* launches);
+void vc_launch_gather_whitened(const VcMatrix& M, int p, double* z_out_dev, cudaStream_t st,
+                               int64_t* launches);
+void vc_launch_extract_chol(const VcMatrix& M, double* r_out_dev, cudaStream_t st,
+                            int64_t* launches);

@@ -1,0 +1,36 @@
+// vc_handle.cuh -- the opaque handle behind the C ABI (shared by vc_api.cu, vc_extra.cu, vc_dist.cu).
+#pragma once
+#include "vc_common.cuh"
+
+struct vc_handle {
+  vc_config cfg;
+  int64_t n = 0, n_pad = 0;
+  int d = 0, p = 0, q = 0;
+  int device = 0;
+  VcMatrix M{};
+  // O(n) inputs, zero-padded to n_pad, column-major
+  double *locs = nullptr, *x = nullptr, *w = nullptr, *y = nullptr;
+  double* mu_in = nullptr;           // staging for caller-supplied mu (p x slots)
+  double* results = nullptr;         // device result records
+  double* results_host = nullptr;    // pinned mirror
+  int result_slots = 0;
+  VcCholWork cw{};
+  VcFinalWork fw{};
+  cudaStream_t st_main = nullptr, st_panel = nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // t0, after build, after chol, after finalize
+  vc_timing last_timing{};
+  int last_info = 0;
+  bool factor_valid = false;
+  int64_t launches = 0;
+  std::string err;
+  // distributed state lives in vc_dist.cu
+  void* dist = nullptr;
+};
+
+
+int vc_make_theta(const vc_handle* h, const double* theta, VcTheta* t);
+vc_handle* vc_alloc_common(const vc_config* cfg, int64_t n, int d, int p, int q, const double* locs,
+                           const double* X, const double* W, const double* y, bool alloc_matrix);
+void vc_free_handle(vc_handle* h);
+int vc_fail(vc_handle* h, int code, const std::string& msg);
+int vc_validate_cfg(const vc_config* cfg, int64_t n, int d, int p, int q, std::string& why);
