@@ -1,0 +1,267 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI (ctypes), against the CPU
+oracle on the same seeded inputs, against the vignette golden values, and -- at sizes the oracle
+cannot reach -- through size-independent properties.
+
+Tolerances (BASELINE.json north_star): 1e-10 relative on -2logL, 1e-6 relative on optimised
+parameters.  Element-wise checks of Sigma / factor / whitened data use 1e-12.
+"""
+import numpy as np
+import pytest
+
+from conftest import synth, theta_for
+
+pytestmark = pytest.mark.gpu
+
+TOL_N2LL = 1e-10
+TOL_PAR = 1e-6
+TOL_ELEM = 1e-12
+
+
+def _rel(a, b):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+
+
+def _oracle():
+    from oracle import svc_oracle as o
+    return o
+
+
+@pytest.mark.parametrize("n,p,cov,dim,lookahead,nb", [
+    (1, 1, "exp", 1, True, 0), (2, 1, "exp", 2, True, 0), (100, 2, "exp", 1, True, 0),
+    (127, 2, "mat32", 2, True, 0), (128, 3, "exp", 2, True, 0), (129, 3, "mat52", 2, False, 0),
+    (640, 3, "sph", 2, True, 256), (1000, 2, "exp", 2, True, 0), (1537, 3, "wend1", 3, True, 128),
+    (2500, 5, "wend2", 2, True, 0), (3000, 3, "mat32", 2, False, 384), (4100, 3, "exp", 2, True, 0),
+])
+def test_n2ll_matches_oracle(n, p, cov, dim, lookahead, nb):
+    o = _oracle()
+    from varycoef_b200 import SVCObjective
+    locs, X, W, y = synth(n, p, 100 + n, dim)
+    theta = theta_for(p)
+    if cov in ("sph", "wend1", "wend2"):
+        theta[0:2 * p:2] *= 3.0   # compact support: keep some neighbours inside the range
+    D = o.own_dist(locs)
+    with SVCObjective(y, X, locs, cov_name=cov, profileLik=True, lookahead=lookahead, nb_outer=nb) as obj:
+        r = obj.n2LL(theta, parts=True)
+        ref = o.n2ll(theta, D, X, W, y, cov, profile=True, faithful=(n <= 1000), parts=True)
+        assert abs(r["n2ll"] - ref["n2ll"]) <= TOL_N2LL * abs(ref["n2ll"])
+        assert abs(r["logdet"] - ref["logdet"]) <= TOL_N2LL * max(abs(ref["logdet"]), n)
+        assert abs(r["quad"] - ref["quad"]) <= TOL_N2LL * max(abs(ref["quad"]), n)
+        assert _rel(r["mu"], ref["mu"]) <= 1e-9
+        # the three mu modes of n2LL (R-pkg/R/objective_functions.R:31-43)
+        mu = ref["mu"] * 1.03 + 0.1
+        v = obj.n2LL(np.concatenate([theta, mu]), profile=False)
+        vr = o.n2ll(np.concatenate([theta, mu]), D, X, W, y, cov, profile=False, faithful=False)
+        assert abs(v - vr) <= TOL_N2LL * abs(vr)
+        v = obj.n2LL(theta, mean_est=mu, profile=True)
+        assert abs(v - vr) <= TOL_N2LL * abs(vr)
+        assert obj.launch_count > 0
+
+
+@pytest.mark.parametrize("n,p,q,cov,dim", [(300, 2, 2, "exp", 1), (777, 3, 2, "mat32", 2), (1300, 2, 4, "mat52", 3)])
+def test_sigma_factor_and_whitened_elementwise(n, p, q, cov, dim):
+    o = _oracle()
+    from scipy.linalg import solve_triangular
+    from varycoef_b200 import SVCObjective
+    locs, X, W, y = synth(n, p, 7 + n, dim, q=q)
+    theta = theta_for(q)
+    D = o.own_dist(locs)
+    with SVCObjective(y, X, locs, W, cov_name=cov, profileLik=True) as obj:
+        S = obj.Sigma_y(theta)
+        Sref = o.sigma_y(theta, D, W, cov)
+        assert _rel(S, Sref) <= TOL_ELEM
+        assert np.array_equal(S, S.T)
+        obj.n2LL(theta)
+        R = obj.chol()
+        Rref = o.chol_upper(Sref)
+        assert np.all(np.tril(R, -1) == 0.0)
+        assert _rel(R, Rref) <= 1e-11
+        Z = obj.whitened()
+        Zref = solve_triangular(Rref, np.column_stack([X, y]), trans=1, lower=False)
+        assert _rel(Z, Zref) <= 1e-10
+
+
+@pytest.mark.parametrize("method,pm", [("maximum", 2.0), ("manhattan", 2.0), ("minkowski", 3.0)])
+def test_dist_methods(method, pm):
+    o = _oracle()
+    from varycoef_b200 import SVCObjective
+    locs, X, W, y = synth(500, 2, 5, 3)
+    theta = theta_for(2)
+    D = o.own_dist(locs, method=method, p=pm)
+    with SVCObjective(y, X, locs, dist={"method": method, "p": pm}, profileLik=True) as obj:
+        assert _rel(obj.Sigma_y(theta), o.sigma_y(theta, D, W, "exp")) <= TOL_ELEM
+        v = obj.n2LL(theta)
+        vr = o.n2ll(theta, D, X, W, y, "exp", profile=True)
+        assert abs(v - vr) <= TOL_N2LL * abs(vr)
+
+
+def test_many_coordinates_and_many_svcs_generic_path():
+    """d > 3 or q > 8 takes the shared-memory (non register-resident) build path."""
+    o = _oracle()
+    from varycoef_b200 import SVCObjective
+    rng = np.random.default_rng(11)
+    n, d, q = 400, 5, 10
+    locs = rng.uniform(0, 3, (n, d))
+    W = np.column_stack([np.ones(n), rng.standard_normal((n, q - 1))])
+    X = W[:, :3]
+    y = rng.standard_normal(n)
+    theta = np.concatenate([np.tile([1.5, 0.3], q), [0.5]])
+    D = o.own_dist(locs)
+    with SVCObjective(y, X, locs, W, cov_name="mat32", profileLik=True) as obj:
+        assert _rel(obj.Sigma_y(theta), o.sigma_y(theta, D, W, "mat32")) <= TOL_ELEM
+        v = obj.n2LL(theta)
+        vr = o.n2ll(theta, D, X, W, y, "mat32", profile=True)
+        assert abs(v - vr) <= TOL_N2LL * abs(vr)
+
+
+def test_vignette_golden_loglik_on_gpu(vignette_train, golden):
+    """Known-answer test: logLik = -106.70, BIC = 231.82 of examples/01_Introduction.html."""
+    from varycoef_b200 import SVCObjective
+    y, X, locs = vignette_train
+    x = np.array(golden["cov_par"] + golden["coef"])
+    with SVCObjective(y, X, locs) as obj:
+        v = obj.n2LL(x)          # default control: exp, non-profile
+        assert round(-v / 2, 2) == golden["logLik_2dp"]
+        assert abs(v + np.log(100) * 4 - golden["BIC"]) < 5e-3
+        o = _oracle()
+        vr = o.n2ll(x, o.own_dist(locs), X, X, y, profile=False)
+        assert abs(v - vr) <= TOL_N2LL * abs(vr)
+
+
+def test_tapered_matches_spam_semantics():
+    """Config 5 in small: Wendland-tapered Sigma built on the GPU (dense with exact zeros) vs the
+    spam-semantics oracle lower.tri + t() + diag (R-pkg/R/utils.R:195-232), and the likelihood."""
+    o = _oracle()
+    from varycoef_b200 import SVCObjective
+    n = 2000
+    locs, X, W, y = synth(n, 3, 55, 2)
+    theta = theta_for(3)
+    delta = 0.6
+    D, mask = o.own_dist(locs, taper=delta)
+    with SVCObjective(y, X, locs, cov_name="exp", tapering=delta, profileLik=True) as obj:
+        S = obj.Sigma_y(theta)
+        Sref = o.sigma_y(theta, D, W, "exp", taper_range=delta, mask=mask)
+        assert _rel(S, Sref) <= TOL_ELEM
+        full_D = o.own_dist(locs)
+        assert np.all(S[full_D >= delta] == 0.0)
+        frac = np.mean(S != 0.0)
+        assert 0.002 < frac < 0.05
+        r = obj.n2LL(theta, parts=True)
+        ref = o.n2ll(theta, D, X, W, y, "exp", taper_range=delta, mask=mask, profile=True, parts=True)
+        assert abs(r["n2ll"] - ref["n2ll"]) <= TOL_N2LL * abs(ref["n2ll"])
+        assert _rel(r["mu"], ref["mu"]) <= 1e-9
+    # mat52 + wend2 taper works for q = 1
+    with SVCObjective(y, X, locs, W[:, :1], cov_name="mat52", tapering=delta, profileLik=True) as obj:
+        th = np.array([1.3, 0.7, 0.35])
+        S = obj.Sigma_y(th)
+        Sref = o.sigma_y(th, D, W[:, :1], "mat52", taper_range=delta, mask=mask)
+        assert _rel(S, Sref) <= TOL_ELEM
+
+
+def test_edge_cases_collocated_zero_variance_and_errors():
+    o = _oracle()
+    from varycoef_b200 import SVCObjective, _lib
+    locs, X, W, y = synth(260, 2, 9, 2)
+    locs[10] = locs[3]          # collocated observations are legal (R-pkg/R/SVC_mle.R:506-508)
+    locs[200] = locs[3]
+    D = o.own_dist(locs)
+    with SVCObjective(y, X, locs, profileLik=True) as obj:
+        theta = theta_for(2)
+        v, vr = obj.n2LL(theta), o.n2ll(theta, D, X, W, y, profile=True)
+        assert abs(v - vr) <= TOL_N2LL * abs(vr)
+        th0 = theta.copy()
+        th0[1] = 0.0            # sigma_k^2 = 0 is the default lower bound, a legal point
+        v, vr = obj.n2LL(th0), o.n2ll(th0, D, X, W, y, profile=True)
+        assert abs(v - vr) <= TOL_N2LL * abs(vr)
+        # not positive definite -> base::chol's error, surfaced as a status, with the minor index
+        bad = theta.copy()
+        bad[-1] = -50.0
+        with pytest.raises(_lib.NotPositiveDefinite, match="leading minor of order"):
+            obj.n2LL(bad)
+        with pytest.raises(np.linalg.LinAlgError):
+            o.n2ll(bad, D, X, W, y, profile=True)
+        bad = theta.copy()
+        bad[0] = 0.0            # range must be > 0
+        with pytest.raises(ValueError):
+            obj.n2LL(bad)
+        with pytest.raises(ValueError):
+            obj.n2LL(theta, profile=False)   # non-profile needs the p means in x
+        # the handle survives errors
+        v, vr = obj.n2LL(theta), o.n2ll(theta, D, X, W, y, profile=True)
+        assert abs(v - vr) <= TOL_N2LL * abs(vr)
+        vals, status = obj.n2LL_batch(np.vstack([theta, bad, theta]), return_status=True)
+        assert list(status) == [0, 2, 0] and np.isnan(vals[1]) and vals[0] == vals[2] == v
+
+
+def test_batch_equals_single_and_is_deterministic():
+    from varycoef_b200 import SVCObjective
+    locs, X, W, y = synth(900, 3, 21, 2)
+    base = theta_for(3)
+    xs = np.vstack([base * (1 + 0.01 * k) for k in range(9)])
+    with SVCObjective(y, X, locs, profileLik=True) as obj:
+        single = np.array([obj.n2LL(x) for x in xs])
+        batch = obj.n2LL_batch(xs)
+        assert np.array_equal(single, batch)
+        assert np.array_equal(batch, obj.n2LL_batch(xs))
+
+
+def test_properties_at_scale_permutation_scaling_and_third_path():
+    """n = 12 000 (beyond what the faithful oracle finishes in seconds): invariances of the
+    Gaussian likelihood plus an independent third path (torch/cuSOLVER Cholesky of the GPU-built
+    Sigma) for log-det and quadratic form."""
+    import torch
+    from varycoef_b200 import SVCObjective
+    n, p = 12000, 3
+    locs, X, W, y = synth(n, p, 77, 2)
+    theta = theta_for(p)
+    with SVCObjective(y, X, locs, profileLik=True) as obj:
+        r = obj.n2LL(theta, parts=True)
+        S = torch.from_numpy(obj.Sigma_y(theta)).cuda()
+    Lt = torch.linalg.cholesky(S)
+    logdet = 2.0 * torch.log(torch.diagonal(Lt)).sum().item()
+    B = torch.from_numpy(np.column_stack([X, y])).cuda()
+    Z = torch.linalg.solve_triangular(Lt, B, upper=False)
+    G = (Z.T @ Z).cpu().numpy()
+    mu = np.linalg.solve(G[:p, :p], G[:p, p])
+    rz = (Z[:, p] - Z[:, :p] @ torch.from_numpy(mu).cuda())
+    quad = float((rz @ rz).item())
+    ref = n * np.log(2 * np.pi) + logdet + quad
+    assert abs(r["n2ll"] - ref) <= TOL_N2LL * abs(ref)
+    assert abs(r["logdet"] - logdet) <= TOL_N2LL * abs(ref)
+    assert _rel(r["mu"], mu) <= 1e-9
+    del S, Lt, Z
+    # permutation of the observations leaves -2logL unchanged
+    perm = np.random.default_rng(0).permutation(n)
+    with SVCObjective(y[perm], X[perm], locs[perm], profileLik=True) as obj2:
+        v2 = obj2.n2LL(theta)
+    assert abs(v2 - r["n2ll"]) <= TOL_N2LL * abs(r["n2ll"])
+    # y -> c y, variances -> c^2 variances  =>  -2logL + n log c^2 ; mu -> c mu
+    c = 3.0
+    th2 = theta.copy()
+    th2[1::2] *= c * c
+    th2[-1] = theta[-1] * c * c
+    with SVCObjective(c * y, X, locs, profileLik=True) as obj3:
+        r3 = obj3.n2LL(th2, parts=True)
+    assert abs(r3["n2ll"] - (r["n2ll"] + n * np.log(c * c))) <= TOL_N2LL * abs(r["n2ll"])
+    assert _rel(r3["mu"], c * r["mu"]) <= 1e-9
+
+
+def test_fit_parameters_match_oracle_fit(vignette_train):
+    """Full optim fit (vignette data, default control) with the GPU objective vs the same driver
+    on the oracle objective: optimised parameters within 1e-6 relative."""
+    o = _oracle()
+    from varycoef_b200.optim import optim_lbfgsb
+    from varycoef_b200.svc_mle import SVC_mle, SVC_mle_control
+    y, X, locs = vignette_train
+    D = o.own_dist(locs)
+    fit = SVC_mle(y, X, locs, control=SVC_mle_control(save_fitted=False), compute_edof=False)
+    liu = o.default_liu(D, X, X, y)
+    assert np.allclose(fit.liu["init"], liu["init"], rtol=1e-14)
+    f = lambda x: o.n2ll(x, D, X, X, y, profile=False, faithful=False)  # noqa: E731
+    ref = optim_lbfgsb(liu["init"], fn=f, lower=liu["lower"], upper=liu["upper"], hessian=True,
+                       control={"parscale": np.abs(liu["init"])})
+    assert fit.optim_output["convergence"] == 0
+    assert abs(fit.optim_output["value"] - ref["value"]) <= TOL_N2LL * abs(ref["value"]) * 10
+    assert np.allclose(fit.optim_output["par"], ref["par"], rtol=TOL_PAR)
+    assert round(fit.logLik(), 2) == -106.70
+    assert abs(fit.BIC() - 231.82) < 5e-3

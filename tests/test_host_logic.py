@@ -1,0 +1,192 @@
+"""CPU-side checks: the C-ABI library loads and exports every declared symbol, the host mirror
+of the reference interface behaves like the reference, and the product never touches oracle/."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    src = open(os.path.join(ROOT, "include", "varycoef_b200.h")).read()
+    return sorted(set(re.findall(r"VC_API\s+[\w\s\*]+?\b(vc_\w+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from varycoef_b200 import _lib
+    L = _lib.lib()
+    syms = _header_symbols()
+    assert len(syms) >= 25
+    for s in syms:
+        assert hasattr(L, s), "symbol %s declared in include/varycoef_b200.h is not exported" % s
+        assert s in _lib.SIGNATURES, "no ctypes signature for %s" % s
+    assert sorted(_lib.SIGNATURES) == syms
+    assert L.vc_abi_version() == 1
+
+
+def test_config_default_and_struct_layout():
+    from varycoef_b200 import _lib
+    cfg = _lib.VcConfig()
+    assert _lib.lib().vc_config_default(C.byref(cfg)) == 0
+    assert (cfg.cov_id, cfg.dist_method, cfg.taper_id, cfg.nb_outer, cfg.flags) == (0, 0, 0, 0, 0)
+    assert cfg.minkowski_p == 2.0
+    assert C.sizeof(_lib.VcConfig) == 40 and C.sizeof(_lib.VcTiming) == 16
+
+
+def test_block_cyclic_maps():
+    L = __import__("varycoef_b200._lib", fromlist=["lib"]).lib()
+    pr, pc = 2, 4
+    seen = {}
+    for bi in range(7):
+        for bj in range(9):
+            r = L.vc_bc_owner(bi, bj, pr, pc)
+            assert r == (bi % pr) * pc + (bj % pc)
+            seen.setdefault(r, 0)
+            seen[r] += 1
+    assert set(seen) == set(range(8))
+    assert [L.vc_bc_local(b, 4) for b in range(9)] == [0, 0, 0, 0, 1, 1, 1, 1, 2]
+    for nblocks in (1, 5, 8, 13):
+        assert sum(L.vc_bc_count(nblocks, c, 4) for c in range(4)) == nblocks
+    assert L.vc_bc_owner(-1, 0, 2, 2) == -1
+
+
+@pytest.mark.skipif(__import__("torch").cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_product_fails_loudly_without_gpu():
+    from varycoef_b200 import SVCObjective, _lib
+    with pytest.raises(_lib.VcError):
+        SVCObjective(np.zeros(10), np.ones((10, 2)), np.arange(10.0))
+
+
+def test_invalid_arguments_rejected_before_touching_the_gpu():
+    from varycoef_b200 import SVCObjective
+    with pytest.raises(ValueError):
+        SVCObjective(np.zeros(10), np.ones((10, 2)), np.arange(10.0), cov_name="gauss")
+    with pytest.raises(ValueError):
+        SVCObjective(np.zeros(10), np.ones((9, 2)), np.arange(10.0))
+    with pytest.raises(ValueError):   # get_taper returns NULL for sph (R-pkg/R/utils.R:545-552)
+        SVCObjective(np.zeros(10), np.ones((10, 2)), np.arange(10.0), cov_name="sph", tapering=1.0)
+    with pytest.raises(ValueError):   # R-pkg/R/utils.R:211 + :3 : mat32 + taper needs q = 1
+        SVCObjective(np.zeros(10), np.ones((10, 2)), np.arange(10.0), cov_name="mat32", tapering=1.0)
+    with pytest.raises(ValueError):
+        SVCObjective(np.zeros(10), np.ones((10, 2)), np.arange(10.0), dist={"method": "canberra"})
+
+
+def test_no_oracle_or_cpu_fallback_in_product():
+    pkg = os.path.join(ROOT, "varycoef_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dp, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+                assert "svc_oracle" not in src, f
+    out = subprocess.run([sys.executable, "-c",
+                          "import sys, varycoef_b200, varycoef_b200.svc_mle, varycoef_b200.optim;"
+                          "print(any(m == 'oracle' or m.startswith('oracle.') for m in sys.modules))"],
+                         cwd=ROOT, capture_output=True, text=True)
+    assert out.stdout.strip() == "False", out.stderr
+
+
+def test_pc_penalty_matches_oracle():
+    from oracle import svc_oracle as o
+    from varycoef_b200 import pc_penalty
+    x = np.array([0.7, 1.2, 2.0, 0.4, 0.3])
+    pcp = (0.5, 0.05, 2.0, 0.1)
+    assert pc_penalty(x, 2, None) == 0.0
+    assert pc_penalty(x, 2, pcp) == pytest.approx(o.pc_penalty(x, 2, pcp), rel=1e-15)
+    lam_r = -np.log(0.05) * 2 * 0.5
+    lam_s = -np.log(0.1) / 2.0
+    ref = sum(4 * np.log(r) + lam_r / r + 2 * lam_s * np.sqrt(s) for r, s in ((0.7, 1.2), (2.0, 0.4)))
+    assert pc_penalty(x, 2, pcp) == pytest.approx(ref, rel=1e-14)
+
+
+def test_check_cov_lower_and_init_bounds():
+    from oracle import svc_oracle as o
+    from varycoef_b200 import check_cov_lower
+    from varycoef_b200.svc_mle import SVC_mle_control, init_bounds_optim
+    assert check_cov_lower([0.1, 0, 0.2, 1, 0.2], 2)
+    assert not check_cov_lower([0, 0, 0.2, 1, 0.2], 2)
+    assert not check_cov_lower([0.1, 0, 0.2, 1, 0], 2)
+    assert not check_cov_lower([0.1, 0, 0.2, -1, 0], 2)
+    for prof in (False, True):
+        ctl = SVC_mle_control(profileLik=prof)
+        liu = init_bounds_optim(ctl, 3, 2, range(5 if prof else 8), 2.5, 4.0, [1.0, 2.0, 3.0])
+        ref = o.init_bounds_optim(3, 2, 2.5, 4.0, [1.0, 2.0, 3.0], prof)
+        for k in ("lower", "init", "upper"):
+            assert np.array_equal(liu[k], ref[k])
+    ctl = SVC_mle_control(init=[1, 1, 1])
+    with pytest.raises(ValueError, match="Initial vector has wrong length"):
+        init_bounds_optim(ctl, 2, 2, range(7), 1.0, 1.0, [0, 0])
+    ctl = SVC_mle_control(lower=[0.0, 0, 0.1, 0, 0.1, 0, 0], profileLik=False)
+    with pytest.raises(ValueError, match="Lower boundary vector is not greater"):
+        init_bounds_optim(ctl, 2, 2, range(7), 1.0, 1.0, [0, 0])
+    with pytest.raises(ValueError):
+        SVC_mle_control(cov_name="gauss")
+    with pytest.raises(ValueError):
+        SVC_mle_control(tapering=-1.0)
+    assert SVC_mle_control()["profileLik"] is False and SVC_mle_control()["hessian"] is True
+
+
+def test_median_dist_exact_small_and_histogram_paths():
+    from varycoef_b200.svc_mle import median_dist
+    from oracle import svc_oracle as o
+    rng = np.random.default_rng(3)
+    for n, d in ((7, 1), (50, 2), (501, 2)):
+        locs = rng.uniform(0, 5, (n, d))
+        assert median_dist(locs) == pytest.approx(float(np.median(o.own_dist(locs))), rel=1e-15)
+    locs = rng.uniform(0, 5, (3200, 2))      # > 4e6 pairs: histogram selection path
+    assert median_dist(locs, block=1024) == pytest.approx(float(np.median(o.own_dist(locs))), rel=1e-15)
+    locs = rng.uniform(0, 5, (60, 3))
+    for m in ("maximum", "manhattan"):
+        assert median_dist(locs, m) == pytest.approx(float(np.median(o.own_dist(locs, method=m))), rel=1e-15)
+
+
+def test_optim_driver_semantics():
+    from varycoef_b200.optim import optim_lbfgsb, optimhess, fd_points
+    # central differences clipped at the bounds, divisor = span actually used (R's fmingr)
+    pts, div = fd_points(np.array([1.0, 0.0005]), np.array([2.0, 1.0]), np.array([1e-3, 1e-3]),
+                         np.array([0.0, 0.0]), np.array([1.0, 1.0]))
+    assert np.allclose(pts[0], [2.0, 0.0005]) and np.allclose(pts[1], [1.998, 0.0005])
+    assert np.allclose(pts[3], [2.0, 0.0]) and np.allclose(div, [1e-3, 1.5e-3])
+    # quadratic: exact Hessian, batch and scalar paths agree
+    A = np.array([[3.0, 0.5], [0.5, 2.0]])
+    f = lambda x: float(x @ A @ x)  # noqa: E731
+    fb = lambda xs: np.array([f(x) for x in xs])  # noqa: E731
+    H = optimhess(np.array([0.3, -0.2]), fn=f, parscale=np.array([2.0, 0.5]))
+    assert np.allclose(H, 2 * A, rtol=1e-6)
+    r1 = optim_lbfgsb([1.0, 1.0], fn=f, hessian=True)
+    r2 = optim_lbfgsb([1.0, 1.0], fn_batch=fb, hessian=True)
+    assert np.allclose(r1["par"], 0, atol=1e-4) and np.allclose(r1["par"], r2["par"])
+    assert r1["convergence"] == 0 and r1["objective_evals"] == r2["objective_evals"]
+    assert r1["objective_evals"] == r1["counts"]["function"] + 4 * r1["counts"]["gradient"] + 16
+    # bound-constrained
+    r = optim_lbfgsb([2.0, 2.0], fn=lambda x: float((x[0] + 1) ** 2 + (x[1] - 3) ** 2), lower=[0, 0], upper=[5, 2.5])
+    assert np.allclose(r["par"], [0.0, 2.5], atol=1e-6)
+    with pytest.raises(FloatingPointError, match="finite values"):
+        optim_lbfgsb([1.0], fn=lambda x: float("nan"))
+
+
+def test_fast_exp_matches_libm():
+    """vc_math.cuh's table-driven exp(-t) (the build kernel's hot op), compiled for the host."""
+    import tempfile
+    src = r'''
+#include "vc_math.cuh"
+#include <stdio.h>
+#include <stdlib.h>
+int main(){ double tab[64]; vc_fill_exp2_table(tab); double mx=0; srand(7);
+ for(long i=0;i<4000000;i++){ double u=rand()/(double)RAND_MAX; int c=i%4;
+  double t = c==0? u*1e-3 : c==1? u*5 : c==2? u*100 : u*707.9;
+  double a=vc_exp_neg(t,tab), b=exp(-t); double r=fabs(a-b)/b; if(r>mx) mx=r; }
+ printf("%.3e %.17g %.17g\n", mx, vc_exp_neg(0.0,tab), vc_exp_neg(800.0,tab)); return 0; }
+'''
+    with tempfile.TemporaryDirectory() as td:
+        cpp = os.path.join(td, "t.cpp")
+        open(cpp, "w").write(src)
+        exe = os.path.join(td, "t")
+        subprocess.check_call(["g++", "-O2", "-x", "c++", "-I", os.path.join(ROOT, "varycoef_b200", "csrc"), cpp, "-o", exe])
+        mx, e0, e800 = subprocess.check_output([exe], text=True).split()
+    assert float(mx) < 4.5e-16 and float(e0) == 1.0 and float(e800) == 0.0
