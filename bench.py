@@ -296,7 +296,7 @@ def run_ours(args):
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     hbm_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "6650 GB/s (of fallback)"
-    roof = {"bound": "tensor", "kernel": "k_gemm<MODE_UPDATE> (DMMA trailing SYRK) inside the bordered Cholesky",
+    roof = {"bound": "tensor", "kernel": "k_syrk_update (DMMA trailing SYRK) inside the bordered Cholesky",
             "achieved": chol_flops / chol_s / 1e12, "peak": peak_tf.value, "unit": "TFLOP/s",
             "frac": chol_flops / chol_s / 1e12 / peak_tf.value if peak_tf.value > 0 else None,
             "traffic": None,

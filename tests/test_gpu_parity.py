@@ -246,22 +246,49 @@ def test_properties_at_scale_permutation_scaling_and_third_path():
     assert _rel(r3["mu"], c * r["mu"]) <= 1e-9
 
 
-def test_fit_parameters_match_oracle_fit(vignette_train):
-    """Full optim fit (vignette data, default control) with the GPU objective vs the same driver
-    on the oracle objective: optimised parameters within 1e-6 relative."""
+def test_vignette_fit_on_gpu(vignette_train, golden):
+    """Full optim fit of the vignette model (default control) driven by the GPU objective.  The
+    likelihood of this n = 100 data set is flat in the range parameters: two bit-different but
+    equally accurate objectives (even the oracle's own faithful / lean variants) end 2e-3 apart
+    in theta under optim's default factr, so this test pins the optimum value and the printed
+    digits, and the 1e-6 parameter tolerance is checked on identified models below."""
+    o = _oracle()
+    from varycoef_b200.svc_mle import SVC_mle, SVC_mle_control
+    y, X, locs = vignette_train
+    fit = SVC_mle(y, X, locs, control=SVC_mle_control(save_fitted=False), compute_edof=False)
+    liu = o.default_liu(o.own_dist(locs), X, X, y)
+    assert np.allclose(fit.liu["init"], liu["init"], rtol=1e-14)
+    assert fit.optim_output["convergence"] == 0
+    assert round(fit.logLik(), 2) == golden["logLik_2dp"]
+    assert abs(fit.BIC() - golden["BIC"]) < 5e-3
+    assert np.allclose(fit.cov_par, golden["cov_par"], rtol=1e-2)
+    assert np.allclose(fit.coef(), golden["coef"], rtol=2e-3)
+    assert np.allclose(np.concatenate([fit.par_SE["RE"]["SE"], fit.par_SE["FE"]["SE"]]),
+                       golden["cov_par_se"] + golden["coef_se"], rtol=2e-2)
+
+
+@pytest.mark.parametrize("q,prof", [(1, True), (1, False), (2, False)])
+def test_fit_parameters_match_oracle_fit(q, prof):
+    """North-star tolerance on optimised parameters (1e-6 relative): the same optim driver on the
+    GPU objective and on the CPU oracle objective, on data simulated from the model
+    (sample_SVCdata, R-pkg/R/example.R:63-134), n = 600."""
     o = _oracle()
     from varycoef_b200.optim import optim_lbfgsb
     from varycoef_b200.svc_mle import SVC_mle, SVC_mle_control
-    y, X, locs = vignette_train
+    rng = np.random.default_rng(5)
+    n = 600
+    locs = rng.uniform(0, 10, (n, 2))
+    d = o.sample_svcdata(rng, locs, [2.0, 1.0][:q] + [0.0] * (2 - q), [1.5, 1.0], [1.0, 2.0], 0.5, "exp")
+    X, y = d["X"], d["y"]
+    W = X[:, :q]
     D = o.own_dist(locs)
-    fit = SVC_mle(y, X, locs, control=SVC_mle_control(save_fitted=False), compute_edof=False)
-    liu = o.default_liu(D, X, X, y)
-    assert np.allclose(fit.liu["init"], liu["init"], rtol=1e-14)
-    f = lambda x: o.n2ll(x, D, X, X, y, profile=False, faithful=False)  # noqa: E731
+    fit = SVC_mle(y, X, locs, W, control=SVC_mle_control(profileLik=prof, save_fitted=False), compute_edof=False)
+    liu = o.default_liu(D, X, W, y, profile_lik=prof)
+    f = lambda x: o.n2ll(x, D, X, W, y, profile=prof, faithful=False)  # noqa: E731
     ref = optim_lbfgsb(liu["init"], fn=f, lower=liu["lower"], upper=liu["upper"], hessian=True,
                        control={"parscale": np.abs(liu["init"])})
-    assert fit.optim_output["convergence"] == 0
-    assert abs(fit.optim_output["value"] - ref["value"]) <= TOL_N2LL * abs(ref["value"]) * 10
+    assert fit.optim_output["convergence"] == 0 and ref["convergence"] == 0
+    assert abs(fit.optim_output["value"] - ref["value"]) <= TOL_N2LL * abs(ref["value"])
     assert np.allclose(fit.optim_output["par"], ref["par"], rtol=TOL_PAR)
-    assert round(fit.logLik(), 2) == -106.70
-    assert abs(fit.BIC() - 231.82) < 5e-3
+    assert np.allclose(fit.optim_output["hessian"], ref["hessian"], rtol=1e-4, atol=1e-4 * np.abs(ref["hessian"]).max())
+    assert fit.optim_output["counts"] == ref["counts"]

@@ -34,7 +34,7 @@ struct BuildArgs {
   VcTheta th;
 };
 
-// shared layout: tab[64] | colX[d][128] | colW[q][128] | rowX[d][128] | rowA[q][128]
+// shared layout: tab[64] | colX[d][128] | colW[q][128] | rowX[d][128] | rowA[q][128] (rowA = W rows)
 template <int COV, bool REG, bool FULL>
 __global__ void __launch_bounds__(BUILD_THREADS) k_build(BuildArgs p) {
   extern __shared__ __align__(16) double sm[];
@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(BUILD_THREADS) k_build(BuildArgs p) {
   for (int idx = tid; idx < q * TILE; idx += BUILD_THREADS) {
     const int k = idx / TILE, r = idx % TILE;
     colW[idx] = p.w[(int64_t)k * p.n_pad + (int64_t)J * TILE + r];
-    rowA[idx] = p.w[(int64_t)k * p.n_pad + (int64_t)I * TILE + r] * p.th.sill[k];
+    rowA[idx] = p.w[(int64_t)k * p.n_pad + (int64_t)I * TILE + r];
   }
   __syncthreads();
 
@@ -77,14 +77,14 @@ __global__ void __launch_bounds__(BUILD_THREADS) k_build(BuildArgs p) {
   const int method = p.th.dist_method;
   const double mink = p.th.mink_p;
 
-  double xi0[RD], xi1[RD], ai0[RQ], ai1[RQ], ir[RQ];
+  double xi0[RD], xi1[RD], ai0[RQ], ai1[RQ], ir[RQ], sk[RQ];
   if (REG) {
 #pragma unroll
     for (int c = 0; c < RD; ++c)
       if (c < d) { xi0[c] = rowX[c * TILE + r0]; xi1[c] = rowX[c * TILE + r0 + 1]; }
 #pragma unroll
     for (int k = 0; k < RQ; ++k)
-      if (k < q) { ai0[k] = rowA[k * TILE + r0]; ai1[k] = rowA[k * TILE + r0 + 1]; ir[k] = p.th.inv_range[k]; }
+      if (k < q) { ai0[k] = rowA[k * TILE + r0]; ai1[k] = rowA[k * TILE + r0 + 1]; ir[k] = p.th.inv_range[k]; sk[k] = p.th.sill[k]; }
   }
 
   for (int cc = 0; cc < 32; ++cc) {
@@ -122,15 +122,17 @@ __global__ void __launch_bounds__(BUILD_THREADS) k_build(BuildArgs p) {
       for (int k = 0; k < RQ; ++k)
         if (k < q) {
           const double wj = colW[k * TILE + j];
-          v0 = fma(ai0[k] * wj, vc_cov_shape<COV>(h0 * ir[k], tab), v0);
-          v1 = fma(ai1[k] * wj, vc_cov_shape<COV>(h1 * ir[k], tab), v1);
+          // (W_ik W_jk) * (sill_k * shape): the reference's Cov * outer.W, exactly symmetric in (i, j)
+          v0 = fma(ai0[k] * wj, sk[k] * vc_cov_shape<COV>(h0 * ir[k], tab), v0);
+          v1 = fma(ai1[k] * wj, sk[k] * vc_cov_shape<COV>(h1 * ir[k], tab), v1);
         }
     } else {
       for (int k = 0; k < q; ++k) {
         const double wj = colW[k * TILE + j];
         const double irk = p.th.inv_range[k];
-        v0 = fma(rowA[k * TILE + r0] * wj, vc_cov_shape<COV>(h0 * irk, tab), v0);
-        v1 = fma(rowA[k * TILE + r0 + 1] * wj, vc_cov_shape<COV>(h1 * irk, tab), v1);
+        const double sk_ = p.th.sill[k];
+        v0 = fma(rowA[k * TILE + r0] * wj, sk_ * vc_cov_shape<COV>(h0 * irk, tab), v0);
+        v1 = fma(rowA[k * TILE + r0 + 1] * wj, sk_ * vc_cov_shape<COV>(h1 * irk, tab), v1);
       }
     }
     if (p.th.taper_id != VC_TAPER_NONE) {

@@ -10,7 +10,7 @@
 //
 // Kernels:
 //   k_potrf128  one CTA: factor a 128x128 diagonal tile in shared memory, also its inverse.
-//   k_gemm<..>  128x128 CTA tile, 8 warps x (64x32) warp tiles, DMMA m8n8k4 (fp64 tensor pipe),
+//   k_trsm_panel / k_syrk_update  128x128 CTA tile, 8 warps x (64x32) warp tiles, DMMA m8n8k4 (fp64 tensor pipe),
 //               4-stage cp.async pipeline.  MODE_TRSM: X = A * Linv^T (panel solve as a GEMM);
 //               MODE_UPDATE: C -= P_I * P_J^T (inner panel update and trailing SYRK).
 #include "vc_common.cuh"
@@ -118,7 +118,7 @@ __device__ __forceinline__ void gemm_mainloop(const double* __restrict__ Ag, int
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm(GemmArgs p) {
+__device__ __forceinline__ void gemm_body(const GemmArgs& p) {
   extern __shared__ __align__(16) double smem[];
   int I, J;
   if (MODE == MODE_TRSM) {
@@ -196,6 +196,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm(GemmArgs p) {
       }
   }
 }
+
+// the two entry points of the DMMA tile kernel (distinct names so profiles read clearly)
+__global__ void __launch_bounds__(GEMM_THREADS, 1) k_trsm_panel(GemmArgs p) { gemm_body<MODE_TRSM>(p); }
+__global__ void __launch_bounds__(GEMM_THREADS, 1) k_syrk_update(GemmArgs p) { gemm_body<MODE_UPDATE>(p); }
 
 // ---------------------------------------------------------------------------------------------
 // k_potrf128: one CTA factors the 128x128 diagonal tile (unblocked right-looking in shared
@@ -293,8 +297,8 @@ void vc_chol_init() {
   VC_CUDA_TRY(cudaGetDevice(&dev));
   bool& done = done_dev[dev & 63];
   if (done) return;
-  VC_CUDA_TRY(cudaFuncSetAttribute(k_gemm<MODE_TRSM>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
-  VC_CUDA_TRY(cudaFuncSetAttribute(k_gemm<MODE_UPDATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+  VC_CUDA_TRY(cudaFuncSetAttribute(k_trsm_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+  VC_CUDA_TRY(cudaFuncSetAttribute(k_syrk_update, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
   VC_CUDA_TRY(cudaFuncSetAttribute(k_potrf128, cudaFuncAttributeMaxDynamicSharedMemorySize, POTRF_SMEM));
   done = true;
 }
@@ -318,7 +322,7 @@ static void launch_update(const VcMatrix& M, int k0, int K, int J0, int J1, cuda
     const int nsb = T + (nsbi - g.nsbj) * g.nsbj;
     grid = (unsigned)nsb * SUPER * SUPER;
   }
-  k_gemm<MODE_UPDATE><<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(g);
+  k_syrk_update<<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(g);
   ++*launches;
 }
 
@@ -346,7 +350,7 @@ void vc_chol_factor(const VcMatrix& M, VcCholWork& w, int64_t* launches) {
       GemmArgs g{};
       g.a = M.a; g.lda = M.lda; g.linv = w.linv + (int64_t)jt * TILE * TILE;
       g.k0 = jt * TILE; g.K = TILE; g.jt = jt; g.nrows = nrows;
-      k_gemm<MODE_TRSM><<<nrows - (jt + 1), GEMM_THREADS, GEMM_SMEM, sp>>>(g);
+      k_trsm_panel<<<nrows - (jt + 1), GEMM_THREADS, GEMM_SMEM, sp>>>(g);
       ++*launches;
       launch_update(M, jt * TILE, TILE, jt + 1, oe, sp, launches);
     }
