@@ -292,3 +292,21 @@ def test_fit_parameters_match_oracle_fit(q, prof):
     assert np.allclose(fit.optim_output["par"], ref["par"], rtol=TOL_PAR)
     assert np.allclose(fit.optim_output["hessian"], ref["hessian"], rtol=1e-4, atol=1e-4 * np.abs(ref["hessian"]).max())
     assert fit.optim_output["counts"] == ref["counts"]
+
+
+@pytest.mark.parametrize("n", [4100, 9000, 20000])
+def test_persistent_update_kernel_bitwise_equals_per_tile_kernel(n):
+    """k_syrk_ws (persistent, TMA-fed, warp-specialised) and k_syrk_tiles (one CTA per tile) run
+    the same DMMA sequence per tile, so -2logL must agree to the last bit, evaluation after
+    evaluation, with and without the lookahead stream."""
+    from varycoef_b200 import SVCObjective
+    locs, X, W, y = synth(n, 3, 1234 + n, 2)
+    theta = theta_for(3)
+    with SVCObjective(y, X, locs, profileLik=True, legacy_syrk=True, lookahead=False) as ref:
+        v_ref = ref.n2LL(theta, parts=True)
+    for la in (True, False):
+        with SVCObjective(y, X, locs, profileLik=True, legacy_syrk=False, lookahead=la) as obj:
+            for rep in range(4):
+                r = obj.n2LL(theta, parts=True)
+                assert r["n2ll"] == v_ref["n2ll"] and r["logdet"] == v_ref["logdet"] and r["quad"] == v_ref["quad"], (la, rep)
+                assert np.array_equal(r["mu"], v_ref["mu"])

@@ -19,6 +19,7 @@ DIST_IDS = {"euclidean": 0, "maximum": 1, "manhattan": 2, "minkowski": 3}
 TAPER_IDS = {None: 0, "wend1": 1, "wend2": 2}
 VC_MU_GLS, VC_MU_FIXED = 0, 1
 VC_FLAG_NO_LOOKAHEAD = 1
+VC_FLAG_LEGACY_SYRK = 2
 
 
 class VcConfig(C.Structure):

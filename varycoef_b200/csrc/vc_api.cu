@@ -58,7 +58,7 @@ void vc_free_handle(vc_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   if (h->dist) vc_dist_destroy(h);
-  cudaFree(h->M.a); cudaFree(h->locs); cudaFree(h->x); cudaFree(h->w); cudaFree(h->y);
+  cudaFree(h->M.a); cudaFree(h->M.b); vc_chol_free_plans(h->cw); cudaFree(h->locs); cudaFree(h->x); cudaFree(h->w); cudaFree(h->y);
   cudaFree(h->mu_in); cudaFree(h->results);
   if (h->results_host) cudaFreeHost(h->results_host);
   cudaFree(h->cw.linv); cudaFree(h->cw.logdet_part); cudaFree(h->cw.info);
@@ -116,11 +116,20 @@ vc_handle* vc_alloc_common(const vc_config* cfg, int64_t n, int d, int p, int q,
     ensure_result_slots(h, 64);
     h->M.n = n; h->M.n_pad = np; h->M.nt = (int)(np / VC_TILE);
     h->M.lda = np + VC_BORDER_ROWS;
+    h->M.nbt = 1;
+    h->M.ldb = VC_BORDER_ROWS;
+    h->cw.legacy_syrk = (cfg->flags & VC_FLAG_LEGACY_SYRK) != 0;
+    {
+      cudaDeviceProp prop;
+      VC_CUDA_TRY(cudaGetDeviceProperties(&prop, h->device));
+      h->cw.num_sms = prop.multiProcessorCount;
+    }
     h->cw.nb_tiles = (cfg->nb_outer > 0 ? cfg->nb_outer : 512) / VC_TILE;
     h->cw.lookahead = !(cfg->flags & VC_FLAG_NO_LOOKAHEAD);
     h->cw.st_main = h->st_main; h->cw.st_panel = h->st_panel;
     if (alloc_matrix) {
       VC_CUDA_TRY(cudaMalloc(&h->M.a, (size_t)h->M.lda * np * sizeof(double)));
+      VC_CUDA_TRY(cudaMalloc(&h->M.b, (size_t)h->M.ldb * np * sizeof(double)));
       VC_CUDA_TRY(cudaMalloc(&h->cw.linv, (size_t)h->M.nt * VC_TILE * VC_TILE * sizeof(double)));
       VC_CUDA_TRY(cudaMalloc(&h->cw.logdet_part, (size_t)h->M.nt * sizeof(double)));
     }

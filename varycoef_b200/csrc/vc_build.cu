@@ -172,8 +172,8 @@ void launch_build_t(const BuildArgs& a, cudaStream_t st) {
 #undef VC_BUILD_CASE
 }
 
-// border rows: A[n_pad + c, j] = X[j, c] (c < p), y[j] (c == p), 0 otherwise
-__global__ void k_border(double* a, int64_t lda, int64_t n_pad, int p, const double* __restrict__ x,
+// border tile 0: B^T[c, j] = X[j, c] (c < p), y[j] (c == p), 0 otherwise
+__global__ void k_border(double* b, int64_t ldb, int64_t n_pad, int p, const double* __restrict__ x,
                          const double* __restrict__ y) {
   const int64_t j = (int64_t)blockIdx.x * 2 + (threadIdx.x >> 7);
   const int c = threadIdx.x & 127;
@@ -181,7 +181,7 @@ __global__ void k_border(double* a, int64_t lda, int64_t n_pad, int p, const dou
   double v = 0.0;
   if (c < p) v = x[(int64_t)c * n_pad + j];
   else if (c == p) v = y[j];
-  a[n_pad + c + j * lda] = v;
+  b[c + j * ldb] = v;
 }
 
 }  // namespace
@@ -219,6 +219,6 @@ void vc_launch_sigma_full(double* out, int64_t n, int64_t n_pad, const VcTheta& 
 
 void vc_launch_border(const VcMatrix& M, int p, const double* x_pad, const double* y_pad,
                       cudaStream_t st, int64_t* launches) {
-  k_border<<<(unsigned)((M.n_pad + 1) / 2), 256, 0, st>>>(M.a, M.lda, M.n_pad, p, x_pad, y_pad);
+  k_border<<<(unsigned)((M.n_pad + 1) / 2), 256, 0, st>>>(M.b, M.ldb, M.n_pad, p, x_pad, y_pad);
   ++*launches;
 }

@@ -4,31 +4,40 @@
 // the border rows, the triangular solves solve(t(R), X), solve(t(R), y), solve(t(R), res) of
 // R-pkg/R/utils.R:94,100 and R-pkg/R/objective_functions.R:49.
 //
-// Storage: lower triangle of Sigma in a column-major (n_pad + 128) x n_pad array; the 128 rows
-// below the matrix hold B^T = [X y]^T.  Running the factorisation over that bordered matrix turns
-// the border into Z^T = (L^-1 B)^T for free (each panel step treats it as one more row tile).
+// Storage: lower triangle of Sigma in a column-major lda x n_pad array `a`; right-hand sides live
+// as ROWS of a separate column-major border array `b` (B^T, 128 rows per border tile).  Sweeping
+// the factorisation over [a; b] turns the border into (L^-1 B)^T for free: every panel step
+// treats a border tile as one more row tile (TRSM + update), it is never factored itself.
 //
 // Kernels:
-//   k_potrf128  one CTA: factor a 128x128 diagonal tile in shared memory, also its inverse.
-//   k_trsm_panel / k_syrk_update  128x128 CTA tile, 8 warps x (64x32) warp tiles, DMMA m8n8k4 (fp64 tensor pipe),
-//               4-stage cp.async pipeline.  MODE_TRSM: X = A * Linv^T (panel solve as a GEMM);
-//               MODE_UPDATE: C -= P_I * P_J^T (inner panel update and trailing SYRK).
+//   k_potrf128     one CTA: factor a 128x128 diagonal tile in shared memory, and invert the factor.
+//   k_trsm_panel   X = A * Linv^T for the row tiles below the diagonal tile: the panel solve as a
+//                  128x128x128 DMMA GEMM (cp.async pipeline).
+//   k_syrk_ws      trailing / inner update C -= P_I P_J^T.  Persistent (one CTA per SM walks a
+//                  precomputed tile list), warp-specialised: one producer warp streams operand
+//                  columns with cp.async.bulk (TMA engine, mbarrier complete_tx), eight consumer
+//                  warps (64x32 warp tiles) issue DMMA m8n8k4 on the fp64 tensor pipe.
+//   k_syrk_tiles   the same update, one CTA per tile with a cp.async pipeline (fallback / A-B).
 #include "vc_common.cuh"
 #include <limits.h>
+#include <algorithm>
+#include <stdlib.h>
 
 namespace {
 
 constexpr int TILE = VC_TILE;
 constexpr int KC = 16;        // k-depth of one pipeline stage
-constexpr int STAGES = 4;
 constexpr int SLD = 132;      // shared-memory stride of one k-column: 128 + 4 doubles -> the
                               // (row, k) fragment pattern of m8n8k4 hits 16 distinct bank pairs
+constexpr int STAGE_DOUBLES = 2 * KC * SLD;                       // A and B operand of one stage
+constexpr int STAGE_BYTES = STAGE_DOUBLES * (int)sizeof(double);  // 33792
 constexpr int GEMM_THREADS = 256;
-constexpr int GEMM_SMEM = 2 * STAGES * KC * SLD * (int)sizeof(double);  // 135168 B
-constexpr int SUPER = 16;     // super-block edge (tiles) of the L2-friendly rasterisation
-
-enum { MODE_TRSM = 0, MODE_UPDATE = 1 };
-enum { RASTER_RECT = 0, RASTER_SUPER = 1 };
+constexpr int STAGES = 4;     // cp.async kernels
+constexpr int GEMM_SMEM = STAGES * STAGE_BYTES;                   // 135168 B
+constexpr int WS_STAGES = 6;  // warp-specialised kernel
+constexpr int WS_THREADS = 288;                                   // 8 consumer warps + 1 producer
+constexpr int WS_SMEM = WS_STAGES * STAGE_BYTES + 2 * WS_STAGES * 8 + 16;
+constexpr int SUPER = 16;     // super-block edge (tiles) of the L2-friendly tile order
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -40,6 +49,40 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
 }
 
+// ---- mbarrier / bulk-copy (TMA engine) helpers -------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem, const void* gmem, unsigned bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                   smem_u32(smem)),
+               "l"(gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void bulk_prefetch_l2(const void* gmem, unsigned bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(gmem), "r"(bytes) : "memory");
+}
+
 // D(8x8) += A(8x4, row) * B(4x8, col) on the fp64 tensor pipe (SASS: DMMA.8x8x4)
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
@@ -48,17 +91,49 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 }
 
 struct GemmArgs {
-  double* a;        // bordered matrix
+  double* a;            // main matrix (row tiles 0 .. nt-1)
   int64_t lda;
-  const double* linv;   // MODE_TRSM: 128x128 inverse factor (ld 128)
-  int k0;           // first panel column (elements)
-  int K;            // panel depth (multiple of KC)
-  int jt;           // MODE_TRSM: panel tile column
-  int J0, J1;       // MODE_UPDATE: tile columns [J0, J1)
-  int nrows;        // number of row tiles incl. border
-  int raster;
-  int nsbj;         // RASTER_SUPER: super-block columns
+  double* b;            // border rows (row tiles nt .. nt+nbt-1)
+  int64_t ldb;
+  int nt;
+  const double* linv;   // TRSM: 128x128 inverse factor (ld 128)
+  int k0;               // first panel column (elements)
+  int K;                // panel depth (multiple of KC)
+  int jt;               // TRSM: panel tile column
+  int n_main;           // TRSM: number of main row tiles handled (0 in solve sweeps)
+  const int* tiles;     // update: packed (I | J << 16)
+  int ntiles;
+  int dbg;              // debug switches (VC_DEBUG env)
 };
+
+// pointer to element (0, col) of row tile I, and its leading dimension
+__device__ __forceinline__ double* row_tile_ptr(const GemmArgs& p, int I, int64_t col, int64_t& ld) {
+  if (I < p.nt) {
+    ld = p.lda;
+    return p.a + (int64_t)I * TILE + col * p.lda;
+  }
+  ld = p.ldb;
+  return p.b + (int64_t)(I - p.nt) * TILE + col * p.ldb;
+}
+
+// one pipeline stage of a warp: 4 k4 steps of 12 fragment loads + 32 DMMA.
+// sa / sb already point at (warp row / col offset + g) of the stage's A / B operand.
+__device__ __forceinline__ void warp_stage(const double* sa, const double* sb, int tig,
+                                           double (&acc)[8][4][2]) {
+#pragma unroll
+  for (int k4 = 0; k4 < KC / 4; ++k4) {
+    const int kk = (k4 * 4 + tig) * SLD;
+    double a[8], b[4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = sa[kk + i * 8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) b[j] = sb[kk + j * 8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+  }
+}
 
 // acc[i][j][0..1]: rows wm*64 + i*8 + (lane>>2), cols wn*32 + j*8 + 2*(lane&3) + {0,1}
 __device__ __forceinline__ void gemm_mainloop(const double* __restrict__ Ag, int64_t lda_a,
@@ -68,13 +143,11 @@ __device__ __forceinline__ void gemm_mainloop(const double* __restrict__ Ag, int
   const int lane = tid & 31, warp = tid >> 5;
   const int wm = warp & 1, wn = warp >> 1;
   const int g = lane >> 2, tig = lane & 3;
-  double* sA = smem;
-  double* sB = smem + STAGES * KC * SLD;
   const int nk = K / KC;
 
   auto load_stage = [&](int slot, int kt) {
-    double* sa = sA + slot * KC * SLD;
-    double* sb = sB + slot * KC * SLD;
+    double* sa = smem + slot * STAGE_DOUBLES;
+    double* sb = sa + KC * SLD;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int id = tid + GEMM_THREADS * i;   // 0..1023
@@ -96,110 +169,171 @@ __device__ __forceinline__ void gemm_mainloop(const double* __restrict__ Ag, int
     const int nxt = kt + STAGES - 1;
     if (nxt < nk) load_stage(nxt % STAGES, nxt);
     cp_async_commit();
-    const int slot = kt % STAGES;
-    const double* sa = sA + slot * KC * SLD + wm * 64 + g;
-    const double* sb = sB + slot * KC * SLD + wn * 32 + g;
-#pragma unroll
-    for (int k4 = 0; k4 < KC / 4; ++k4) {
-      const int kk = (k4 * 4 + tig) * SLD;
-      double a[8], b[4];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) a[i] = sa[kk + i * 8];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) b[j] = sb[kk + j * 8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
-    }
+    const double* sa = smem + (kt % STAGES) * STAGE_DOUBLES;
+    warp_stage(sa + wm * 64 + g, sa + KC * SLD + wn * 32 + g, tig, acc);
   }
   cp_async_wait<0>();
   __syncthreads();
 }
 
-template <int MODE>
-__device__ __forceinline__ void gemm_body(const GemmArgs& p) {
+// ---- panel solve: X(I, jt) = A(I, jt) * Linv^T ------------------------------------------------
+__global__ void __launch_bounds__(GEMM_THREADS, 1) k_trsm_panel(GemmArgs p) {
   extern __shared__ __align__(16) double smem[];
-  int I, J;
-  if (MODE == MODE_TRSM) {
-    I = p.jt + 1 + blockIdx.x;
-    J = p.jt;
-  } else if (p.raster == RASTER_RECT) {
-    const int nr = p.nrows - p.J0;
-    J = p.J0 + blockIdx.x / nr;
-    I = p.J0 + blockIdx.x % nr;
-    if (I < J) return;
-  } else {
-    // super-blocks of SUPER x SUPER tiles, enumerated row by row over the lower trapezoid
-    const int s = blockIdx.x / (SUPER * SUPER);
-    const int w = blockIdx.x % (SUPER * SUPER);
-    const int T = p.nsbj * (p.nsbj + 1) / 2;
-    int sbi, sbj;
-    if (s < T) {
-      sbi = (int)((sqrt(8.0 * s + 1.0) - 1.0) * 0.5);
-      while ((sbi + 1) * (sbi + 2) / 2 <= s) ++sbi;
-      while (sbi * (sbi + 1) / 2 > s) --sbi;
-      sbj = s - sbi * (sbi + 1) / 2;
-    } else {
-      sbi = p.nsbj + (s - T) / p.nsbj;
-      sbj = (s - T) % p.nsbj;
-    }
-    I = p.J0 + sbi * SUPER + (w % SUPER);
-    J = p.J0 + sbj * SUPER + (w / SUPER);
-    if (J >= p.J1 || I >= p.nrows || I < J) return;
-  }
-
+  const int I = ((int)blockIdx.x < p.n_main) ? p.jt + 1 + blockIdx.x : p.nt + (blockIdx.x - p.n_main);
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
   const int wm = warp & 1, wn = warp >> 1;
   const int g = lane >> 2, tig = lane & 3;
-
+  int64_t ld;
+  double* Ct = row_tile_ptr(p, I, (int64_t)p.jt * TILE, ld);
   double acc[8][4][2];
-  double* Ct = p.a + (int64_t)I * TILE + (int64_t)J * TILE * p.lda;
-  double* cbase = Ct + (wm * 64 + g) + (int64_t)(wn * 32 + 2 * tig) * p.lda;
-
-  if (MODE == MODE_UPDATE) {
-    // acc starts at -C so that the epilogue is a pure store: C_new = -(-C + sum a b)
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+  for (int i = 0; i < 8; ++i)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const double* c = cbase + i * 8 + (int64_t)(j * 8) * p.lda;
-        acc[i][j][0] = -c[0];
-        acc[i][j][1] = -c[p.lda];
-      }
-    const double* Pi = p.a + (int64_t)I * TILE + (int64_t)p.k0 * p.lda;
-    const double* Pj = p.a + (int64_t)J * TILE + (int64_t)p.k0 * p.lda;
-    gemm_mainloop(Pi, p.lda, Pj, p.lda, p.K, acc, smem);
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+  // the B operand element (n, k) is Linv[n + 128 k]
+  gemm_mainloop(Ct, ld, p.linv, TILE, TILE, acc, smem);
+  double* cbase = Ct + (wm * 64 + g) + (int64_t)(wn * 32 + 2 * tig) * ld;
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+  for (int i = 0; i < 8; ++i)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        double* c = cbase + i * 8 + (int64_t)(j * 8) * p.lda;
-        c[0] = -acc[i][j][0];
-        c[p.lda] = -acc[i][j][1];
-      }
-  } else {
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-    // X(I, jt) = A(I, jt) * Linv^T : the B operand element (n, k) is Linv[n + 128 k]
-    gemm_mainloop(Ct, p.lda, p.linv, TILE, TILE, acc, smem);
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        double* c = cbase + i * 8 + (int64_t)(j * 8) * p.lda;
-        c[0] = acc[i][j][0];
-        c[p.lda] = acc[i][j][1];
-      }
-  }
+    for (int j = 0; j < 4; ++j) {
+      double* c = cbase + i * 8 + (int64_t)(j * 8) * ld;
+      c[0] = acc[i][j][0];
+      c[ld] = acc[i][j][1];
+    }
 }
 
-// the two entry points of the DMMA tile kernel (distinct names so profiles read clearly)
-__global__ void __launch_bounds__(GEMM_THREADS, 1) k_trsm_panel(GemmArgs p) { gemm_body<MODE_TRSM>(p); }
-__global__ void __launch_bounds__(GEMM_THREADS, 1) k_syrk_update(GemmArgs p) { gemm_body<MODE_UPDATE>(p); }
+// ---- update, one CTA per tile (fallback) ------------------------------------------------------
+__global__ void __launch_bounds__(GEMM_THREADS, 1) k_syrk_tiles(GemmArgs p) {
+  extern __shared__ __align__(16) double smem[];
+  const int packed = p.tiles[blockIdx.x];
+  const int I = packed & 0xffff, J = packed >> 16;
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int wm = warp & 1, wn = warp >> 1;
+  const int g = lane >> 2, tig = lane & 3;
+  int64_t ldc, ldpi, ldpj;
+  double* Ct = row_tile_ptr(p, I, (int64_t)J * TILE, ldc);
+  const double* Pi = row_tile_ptr(p, I, p.k0, ldpi);
+  const double* Pj = row_tile_ptr(p, J, p.k0, ldpj);
+  double* cbase = Ct + (wm * 64 + g) + (int64_t)(wn * 32 + 2 * tig) * ldc;
+  double acc[8][4][2];
+  // acc starts at -C so that the epilogue is a pure store: C_new = -(-C + sum a b)
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const double* c = cbase + i * 8 + (int64_t)(j * 8) * ldc;
+      acc[i][j][0] = -c[0];
+      acc[i][j][1] = -c[ldc];
+    }
+  gemm_mainloop(Pi, ldpi, Pj, ldpj, p.K, acc, smem);
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      double* c = cbase + i * 8 + (int64_t)(j * 8) * ldc;
+      c[0] = -acc[i][j][0];
+      c[ldc] = -acc[i][j][1];
+    }
+}
+
+// ---- update, persistent + warp-specialised ----------------------------------------------------
+// shared: WS_STAGES x [A: KC x SLD | B: KC x SLD] doubles, then full[WS_STAGES], empty[WS_STAGES].
+// Producer (warp 8): per stage, lane l streams k-column (l & 15) of operand (l >> 4) -- one
+// 1-KB cp.async.bulk each -- into the slot, completion counted on full[slot].  Consumers wait on
+// full[slot], run 4 k4 steps, and one lane per warp arrives on empty[slot].  No CTA-wide barrier
+// in steady state: warps drift apart and keep the DMMA pipe fed across stage and tile boundaries.
+__global__ void __launch_bounds__(WS_THREADS, 1) k_syrk_ws(GemmArgs p) {
+  extern __shared__ __align__(16) double smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + WS_STAGES * STAGE_DOUBLES);
+  uint64_t* empty = full + WS_STAGES;
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) {
+    for (int s = 0; s < WS_STAGES; ++s) {
+      mbar_init(full + s, 1);
+      mbar_init(empty + s, 8);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    // the TMA engine updates the barriers (complete_tx) through the async proxy: make the
+    // initialisation visible there before the first bulk copy can land
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+  }
+  __syncthreads();
+  const int nk = p.K / KC;
+
+  if (warp == 8) {
+    // ===== producer =====
+    unsigned it = 0;
+    const int col = lane & 15, opnd = lane >> 4;
+    for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
+      const int packed = p.tiles[t];
+      const int I = packed & 0xffff, J = packed >> 16;
+      int64_t ldsrc;
+      const double* src = row_tile_ptr(p, opnd == 0 ? I : J, p.k0 + col, ldsrc);
+      // pull the NEXT tile's C into L2 while this tile computes (its loads then hit L2)
+      const int tn = t + gridDim.x;
+      if (tn < p.ntiles && !(p.dbg & 1)) {
+        const int pk = p.tiles[tn];
+        int64_t ldn;
+        const double* cn = row_tile_ptr(p, pk & 0xffff, (int64_t)(pk >> 16) * TILE, ldn);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) bulk_prefetch_l2(cn + (int64_t)(lane * 4 + c) * ldn, TILE * 8);
+      }
+      for (int kt = 0; kt < nk; ++kt, ++it) {
+        const unsigned slot = it % WS_STAGES;
+        const unsigned round = it / WS_STAGES;
+        mbar_wait(empty + slot, (round & 1) ^ 1);
+        __syncwarp();
+        if (lane == 0) mbar_expect_tx(full + slot, 2 * KC * TILE * 8);
+        __syncwarp();
+        double* dst = smem + slot * STAGE_DOUBLES + opnd * (KC * SLD) + col * SLD;
+        bulk_g2s(dst, src + (int64_t)kt * KC * ldsrc, TILE * 8, full + slot);
+      }
+    }
+  } else {
+    // ===== consumers =====
+    const int wm = warp & 1, wn = warp >> 1;
+    const int g = lane >> 2, tig = lane & 3;
+    unsigned it = 0;
+    for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
+      const int packed = p.tiles[t];
+      const int I = packed & 0xffff, J = packed >> 16;
+      int64_t ldc;
+      double* Ct = row_tile_ptr(p, I, (int64_t)J * TILE, ldc);
+      double* cbase = Ct + (wm * 64 + g) + (int64_t)(wn * 32 + 2 * tig) * ldc;
+      double acc[8][4][2];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const double* c = cbase + i * 8 + (int64_t)(j * 8) * ldc;
+          acc[i][j][0] = -c[0];
+          acc[i][j][1] = -c[ldc];
+        }
+      for (int kt = 0; kt < nk; ++kt, ++it) {
+        const unsigned slot = it % WS_STAGES;
+        mbar_wait(full + slot, (it / WS_STAGES) & 1);
+        __syncwarp();   // lanes may leave the polling loop in different iterations; mma.sync needs convergence
+        const double* sa = smem + slot * STAGE_DOUBLES;
+        warp_stage(sa + wm * 64 + g, sa + KC * SLD + wn * 32 + g, tig, acc);
+        if (p.dbg & 2) asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + slot);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          double* c = cbase + i * 8 + (int64_t)(j * 8) * ldc;
+          c[0] = -acc[i][j][0];
+          c[ldc] = -acc[i][j][1];
+        }
+    }
+  }
+}
 
 // ---------------------------------------------------------------------------------------------
 // k_potrf128: one CTA factors the 128x128 diagonal tile (unblocked right-looking in shared
@@ -289,6 +423,73 @@ k_potrf128(double* __restrict__ At, int64_t lda, int jt, double* __restrict__ li
 
 __global__ void k_reset_info(int* info) { *info = INT_MAX; }
 
+// ---- host: tile lists -------------------------------------------------------------------------
+// lower trapezoid J in [J0, J1), I in [J, nrows): valid tiles only, super-block by super-block
+// (row of super-blocks by row), I fastest inside a super-block, so that the ~148 tiles in flight
+// share a handful of panel row blocks in L2.
+void append_trapezoid(std::vector<int>& out, int J0, int J1, int nrows) {
+  const int nsbi = (nrows - J0 + SUPER - 1) / SUPER;
+  const int nsbj = (J1 - J0 + SUPER - 1) / SUPER;
+  for (int sbi = 0; sbi < nsbi; ++sbi)
+    for (int sbj = 0; sbj <= sbi && sbj < nsbj; ++sbj)
+      for (int tj = 0; tj < SUPER; ++tj) {
+        const int J = J0 + sbj * SUPER + tj;
+        if (J >= J1) break;
+        for (int ti = 0; ti < SUPER; ++ti) {
+          const int I = J0 + sbi * SUPER + ti;
+          if (I >= nrows) break;
+          if (I >= J) out.push_back(I | (J << 16));
+        }
+      }
+}
+// border rows only: I in [nt, nrows), J in [J0, J1)
+void append_border(std::vector<int>& out, int J0, int J1, int nt, int nrows) {
+  for (int J = J0; J < J1; ++J)
+    for (int I = nt; I < nrows; ++I) out.push_back(I | (J << 16));
+}
+
+void build_plan(VcCholPlan& pl, int nt, int nbt, int nb, bool lookahead, int mode) {
+  if (pl.nt == nt && pl.nbt == nbt && pl.nb == nb && pl.lookahead == lookahead && pl.mode == mode) return;
+  if (nt + nbt > 0x7fff) throw VcError(VC_ERR_INVALID, "matrix too large for the packed tile index");
+  std::vector<int> tiles;
+  pl.calls.clear();
+  const int nrows = nt + nbt;
+  auto add = [&](int k0, int K, int J0, int J1) {
+    VcUpdateCall c;
+    c.k0 = k0; c.K = K; c.tile_off = (int64_t)tiles.size();
+    if (J1 > J0) {
+      if (mode == VC_SWEEP_FACTOR) append_trapezoid(tiles, J0, J1, nrows);
+      else append_border(tiles, J0, J1, nt, nrows);
+    }
+    c.ntiles = (int)((int64_t)tiles.size() - c.tile_off);
+    pl.calls.push_back(c);
+  };
+  // must mirror the launch order of vc_chol_factor exactly
+  for (int ob = 0; ob < nt; ob += nb) {
+    const int oe = std::min(ob + nb, nt);
+    for (int jt = ob; jt < oe; ++jt) add(jt * TILE, TILE, jt + 1, oe);
+    if (oe >= nt) break;
+    const int K = (oe - ob) * TILE;
+    if (!lookahead) {
+      add(ob * TILE, K, oe, nt);
+    } else {
+      const int ne = std::min(oe + nb, nt);
+      add(ob * TILE, K, oe, ne);
+      add(ob * TILE, K, ne, nt);
+    }
+  }
+  if ((int64_t)tiles.size() > pl.tiles_cap) {
+    if (pl.tiles_dev) cudaFree(pl.tiles_dev);
+    pl.tiles_dev = nullptr;
+    pl.tiles_cap = 0;
+    VC_CUDA_TRY(cudaMalloc(&pl.tiles_dev, std::max<size_t>(tiles.size(), 1) * sizeof(int)));
+    pl.tiles_cap = (int64_t)tiles.size();
+  }
+  if (!tiles.empty())
+    VC_CUDA_TRY(cudaMemcpy(pl.tiles_dev, tiles.data(), tiles.size() * sizeof(int), cudaMemcpyHostToDevice));
+  pl.nt = nt; pl.nbt = nbt; pl.nb = nb; pl.lookahead = lookahead; pl.mode = mode;
+}
+
 }  // namespace
 
 void vc_chol_init() {
@@ -298,86 +499,128 @@ void vc_chol_init() {
   bool& done = done_dev[dev & 63];
   if (done) return;
   VC_CUDA_TRY(cudaFuncSetAttribute(k_trsm_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
-  VC_CUDA_TRY(cudaFuncSetAttribute(k_syrk_update, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+  VC_CUDA_TRY(cudaFuncSetAttribute(k_syrk_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+  VC_CUDA_TRY(cudaFuncSetAttribute(k_syrk_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM));
   VC_CUDA_TRY(cudaFuncSetAttribute(k_potrf128, cudaFuncAttributeMaxDynamicSharedMemorySize, POTRF_SMEM));
   done = true;
 }
 
-static void launch_update(const VcMatrix& M, int k0, int K, int J0, int J1, cudaStream_t st,
-                          int64_t* launches) {
-  if (J1 <= J0) return;
+void vc_chol_free_plans(VcCholWork& w) {
+  if (w.plan_factor.tiles_dev) cudaFree(w.plan_factor.tiles_dev);
+  if (w.plan_solve.tiles_dev) cudaFree(w.plan_solve.tiles_dev);
+  w.plan_factor = VcCholPlan();
+  w.plan_solve = VcCholPlan();
+}
+
+static int vc_debug_flags() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("VC_DEBUG"); v = e ? atoi(e) : 0; }
+  return v;
+}
+
+static GemmArgs base_args(const VcMatrix& M) {
   GemmArgs g{};
-  g.a = M.a; g.lda = M.lda; g.linv = nullptr; g.k0 = k0; g.K = K; g.jt = 0;
-  g.J0 = J0; g.J1 = J1; g.nrows = M.nt + 1;
-  const int nj = J1 - J0;
-  unsigned grid;
-  if (nj < SUPER) {
-    g.raster = RASTER_RECT; g.nsbj = 0;
-    grid = (unsigned)nj * (unsigned)(g.nrows - J0);
+  g.dbg = vc_debug_flags();
+  g.a = M.a; g.lda = M.lda; g.b = M.b; g.ldb = M.ldb; g.nt = M.nt;
+  return g;
+}
+
+static void launch_update(const VcMatrix& M, const VcCholWork& w, const VcCholPlan& pl, size_t call,
+                          cudaStream_t st, int64_t* launches, int reserve_sms = 0) {
+  const VcUpdateCall& c = pl.calls[call];
+  if (c.ntiles == 0) return;
+  GemmArgs g = base_args(M);
+  g.k0 = c.k0; g.K = c.K; g.tiles = pl.tiles_dev + c.tile_off; g.ntiles = c.ntiles;
+  if (w.legacy_syrk) {
+    k_syrk_tiles<<<c.ntiles, GEMM_THREADS, GEMM_SMEM, st>>>(g);
   } else {
-    g.raster = RASTER_SUPER;
-    g.nsbj = (nj + SUPER - 1) / SUPER;
-    const int nsbi = (g.nrows - J0 + SUPER - 1) / SUPER;
-    const int T = g.nsbj * (g.nsbj + 1) / 2;
-    const int nsb = T + (nsbi - g.nsbj) * g.nsbj;
-    grid = (unsigned)nsb * SUPER * SUPER;
+    const int grid = std::min(c.ntiles, std::max(w.num_sms - reserve_sms, 1));
+    k_syrk_ws<<<grid, WS_THREADS, WS_SMEM, st>>>(g);
   }
-  k_syrk_update<<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(g);
   ++*launches;
 }
 
-// Factor the bordered matrix.  Two-level blocking: 128-wide sub-panels (potrf128 + TRSM-as-GEMM +
+// A persistent update kernel keeps every SM it starts on until it is done, so the lookahead panel
+// (other stream) only overlaps if some SMs are left free.  Pick the number R of SMs to leave to the
+// panel so that max(panel time on R SMs, trailing update on num_sms - R SMs) is smallest.
+static int pick_reserved_sms(int num_sms, int rows_t /*row tiles below the panel*/, int nb,
+                             int rest_tiles) {
+  if (rest_tiles <= 0) return 0;
+  const double t_potrf = 60.0, t_tile128 = 20.0, t_tile_nb = 17.0 * nb;   // microseconds
+  const double panel_serial = nb * t_potrf;
+  const double panel_par = (nb + nb * (nb - 1) / 2.0) * rows_t * t_tile128;
+  int best = 0;
+  double best_t = 1e300;
+  for (int r = 1; r <= num_sms / 2; ++r) {
+    const double tp = panel_serial + panel_par / r;
+    const double tu = (double)((rest_tiles + (num_sms - r) - 1) / (num_sms - r)) * t_tile_nb;
+    const double t = std::max(tp, tu);
+    if (t < best_t) { best_t = t; best = r; }
+  }
+  return best;
+}
+
+// Sweep the bordered matrix.  Two-level blocking: 128-wide sub-panels (potrf128 + TRSM-as-GEMM +
 // inner update of the rest of the outer block, K = 128) inside nb-wide outer blocks whose
 // trailing SYRK runs with K = nb.  With lookahead the next outer block's columns are updated
-// first and its panel is factored on a second stream while the rest of the trailing matrix
-// is still being updated.
-void vc_chol_factor(const VcMatrix& M, VcCholWork& w, int64_t* launches) {
-  const int nt = M.nt, nrows = nt + 1, nb = w.nb_tiles;
-  cudaStream_t sm = w.st_main, sp = w.lookahead ? w.st_panel : w.st_main;
-  k_reset_info<<<1, 1, 0, sm>>>(w.info);
-  ++*launches;
-  if (w.lookahead) {
+// first and its panel is factored on a second (high-priority) stream while the rest of the
+// trailing matrix is still being updated.  mode VC_SWEEP_SOLVE reuses a resident factor (and the
+// stored diagonal inverses) and sweeps only the border rows: a blocked forward substitution.
+void vc_chol_factor(const VcMatrix& M, VcCholWork& w, int64_t* launches, int mode) {
+  const int nt = M.nt, nbt = M.nbt, nb = w.nb_tiles;
+  const bool solve = (mode == VC_SWEEP_SOLVE);
+  const bool la = w.lookahead && !solve;
+  VcCholPlan& pl = solve ? w.plan_solve : w.plan_factor;
+  build_plan(pl, nt, nbt, nb, la, mode);
+  cudaStream_t sm = w.st_main, sp = la ? w.st_panel : w.st_main;
+  if (!solve) {
+    k_reset_info<<<1, 1, 0, sm>>>(w.info);
+    ++*launches;
+  }
+  if (la) {
     VC_CUDA_TRY(cudaEventRecord(w.ev_update, sm));
     VC_CUDA_TRY(cudaStreamWaitEvent(sp, w.ev_update, 0));
   }
+  size_t call = 0;
   for (int ob = 0; ob < nt; ob += nb) {
-    const int oe = (ob + nb < nt) ? ob + nb : nt;
+    const int oe = std::min(ob + nb, nt);
     // ---- panel: columns [ob, oe) on the panel stream ----
     for (int jt = ob; jt < oe; ++jt) {
-      double* diag = M.a + (int64_t)jt * TILE * (M.lda + 1);
-      k_potrf128<<<1, POTRF_THREADS, POTRF_SMEM, sp>>>(diag, M.lda, jt, w.linv, w.logdet_part, w.info);
-      ++*launches;
-      GemmArgs g{};
-      g.a = M.a; g.lda = M.lda; g.linv = w.linv + (int64_t)jt * TILE * TILE;
-      g.k0 = jt * TILE; g.K = TILE; g.jt = jt; g.nrows = nrows;
-      k_trsm_panel<<<nrows - (jt + 1), GEMM_THREADS, GEMM_SMEM, sp>>>(g);
-      ++*launches;
-      launch_update(M, jt * TILE, TILE, jt + 1, oe, sp, launches);
+      if (!solve) {
+        double* diag = M.a + (int64_t)jt * TILE * (M.lda + 1);
+        k_potrf128<<<1, POTRF_THREADS, POTRF_SMEM, sp>>>(diag, M.lda, jt, w.linv, w.logdet_part, w.info);
+        ++*launches;
+      }
+      GemmArgs g = base_args(M);
+      g.linv = w.linv + (int64_t)jt * TILE * TILE;
+      g.k0 = jt * TILE; g.K = TILE; g.jt = jt;
+      g.n_main = solve ? 0 : nt - (jt + 1);
+      const int grid = g.n_main + nbt;
+      if (grid > 0) {
+        k_trsm_panel<<<grid, GEMM_THREADS, GEMM_SMEM, sp>>>(g);
+        ++*launches;
+      }
+      launch_update(M, w, pl, call++, sp, launches);
     }
     if (oe >= nt) break;
-    const int K = (oe - ob) * TILE;
-    if (!w.lookahead) {
-      launch_update(M, ob * TILE, K, oe, nt, sm, launches);
+    if (!la) {
+      launch_update(M, w, pl, call++, sm, launches);
     } else {
       // panel [ob, oe) is final on sp; main stream waits for it
       VC_CUDA_TRY(cudaEventRecord(w.ev_panel, sp));
       VC_CUDA_TRY(cudaStreamWaitEvent(sm, w.ev_panel, 0));
-      const int ne = (oe + nb < nt) ? oe + nb : nt;
       // next panel's columns first ...
-      launch_update(M, ob * TILE, K, oe, ne, sm, launches);
+      launch_update(M, w, pl, call++, sm, launches);
       VC_CUDA_TRY(cudaEventRecord(w.ev_col, sm));
-      // ... then the rest of the trailing matrix, overlapping the next panel on sp
-      launch_update(M, ob * TILE, K, ne, nt, sm, launches);
-      VC_CUDA_TRY(cudaEventRecord(w.ev_update, sm));
+      // ... then the rest of the trailing matrix, overlapping the next panel on sp.  The next
+      // panel only touches columns [oe, ne), which the rest update neither reads nor writes.
+      const int rest_tiles = pl.calls[call].ntiles;
+      const int reserve = w.legacy_syrk ? 0 : pick_reserved_sms(w.num_sms, nt + nbt - oe, nb, rest_tiles);
+      launch_update(M, w, pl, call++, sm, launches, reserve);
       VC_CUDA_TRY(cudaStreamWaitEvent(sp, w.ev_col, 0));
-      // the next panel's inner updates (and TRSM of lower row tiles) only touch columns
-      // [oe, ne), which the "rest" update does not write; but the step after that must see the
-      // rest update finished -> the panel stream also waits for ev_update before ITS trailing
-      // columns are touched again.  That ordering is enforced at the top of the next iteration:
-      // the update of step ob+1 is issued on sm, after ev_panel of that step.
     }
   }
-  if (w.lookahead) {
+  if (la) {
     VC_CUDA_TRY(cudaEventRecord(w.ev_panel, sp));
     VC_CUDA_TRY(cudaStreamWaitEvent(sm, w.ev_panel, 0));
   }

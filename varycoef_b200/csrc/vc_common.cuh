@@ -52,12 +52,15 @@ struct VcError {
 };
 
 // ---- launchers implemented in the .cu files ------------------------------------------------
-struct VcMatrix {        // bordered, padded, column-major Sigma / factor in HBM
-  double* a;             // (n_pad + VC_BORDER_ROWS) x n_pad
-  int64_t lda;           // n_pad + VC_BORDER_ROWS
+struct VcMatrix {        // padded, column-major Sigma / factor in HBM, plus its border rows
+  double* a;             // lda x n_pad, lower triangle used
+  int64_t lda;           // n_pad + 128 (keeps the column stride off a power of two)
   int64_t n;             // real order
   int64_t n_pad;         // multiple of VC_TILE
   int nt;                // n_pad / VC_TILE  (column tiles)
+  double* b;             // border: (128 * nbt) x n_pad column-major; rows = right-hand sides B^T,
+  int64_t ldb;           //         turned into (L^-1 B)^T by the factorisation / solve sweep
+  int nbt;               // border row tiles in use
 };
 
 // vc_build.cu
@@ -71,17 +74,35 @@ void vc_launch_sigma_full(double* out, int64_t n, int64_t n_pad, const VcTheta& 
 void vc_build_init();
 
 // vc_chol.cu
+struct VcUpdateCall {     // one trailing / inner update of the factorisation plan
+  int k0, K;             // panel columns [k0, k0 + K)
+  int64_t tile_off;      // into the device tile list
+  int ntiles;
+};
+struct VcCholPlan {       // tile lists of every update launch, precomputed per (nt, nbt, nb, mode)
+  int nt = -1, nbt = -1, nb = -1, mode = -1;
+  bool lookahead = false;
+  std::vector<VcUpdateCall> calls;
+  int* tiles_dev = nullptr;          // packed (I | J << 16), L2-friendly super-block order
+  int64_t tiles_cap = 0;
+};
 struct VcCholWork {
   double* linv;          // nt x (128 x 128): inverse of every diagonal factor tile
   double* logdet_part;   // nt partial sums of log L_jj
   int* info;             // first failing leading minor (INT_MAX if none)
   int nb_tiles;          // outer block in tiles (nb_outer / 128)
   bool lookahead;
+  bool legacy_syrk;      // use the non-persistent cp.async SYRK kernel (A/B testing)
+  int num_sms;
   cudaStream_t st_main, st_panel;
   cudaEvent_t ev_panel, ev_update, ev_col;
+  VcCholPlan plan_factor, plan_solve;
 };
+enum { VC_SWEEP_FACTOR = 0,   // potrf + TRSM + updates on every row tile (main + border)
+       VC_SWEEP_SOLVE = 1 };  // factor already resident: only the border rows are swept
 void vc_chol_init();
-void vc_chol_factor(const VcMatrix& M, VcCholWork& w, int64_t* launches);
+void vc_chol_factor(const VcMatrix& M, VcCholWork& w, int64_t* launches, int mode = VC_SWEEP_FACTOR);
+void vc_chol_free_plans(VcCholWork& w);
 
 // vc_finalize.cu
 struct VcFinalWork {

@@ -36,7 +36,7 @@ __device__ __forceinline__ void dd_add(double& hi, double& lo, double ah, double
 
 // partial Gram of the (p+1) border rows over a slice of columns; pairs (a <= b) are linearised
 __global__ void __launch_bounds__(FIN_THREADS)
-k_gram_partial(const double* __restrict__ a, int64_t lda, int64_t n_pad, int64_t n, int p,
+k_gram_partial(const double* __restrict__ b, int64_t ldb, int64_t n, int p,
                double* __restrict__ part) {
   extern __shared__ double sm[];
   const int m = p + 1;
@@ -54,7 +54,7 @@ k_gram_partial(const double* __restrict__ a, int64_t lda, int64_t n_pad, int64_t
     for (int i = tid; i < m * CHUNK; i += FIN_THREADS) {
       const int c = i % m, jj = i / m;
       const int64_t j = jb + jj;
-      z[c * CHUNK + jj] = (j < j1) ? a[n_pad + c + j * lda] : 0.0;
+      z[c * CHUNK + jj] = (j < j1) ? b[c + j * ldb] : 0.0;
     }
     __syncthreads();
     for (int pi = tid; pi < npairs; pi += FIN_THREADS) {
@@ -150,7 +150,7 @@ k_solve_mu(const double* __restrict__ part, int blocks, int p, int mu_mode,
 
 // partial sums of (Z_y - Z_X mu)^2 over a slice of columns
 __global__ void __launch_bounds__(FIN_THREADS)
-k_quad_partial(const double* __restrict__ a, int64_t lda, int64_t n_pad, int64_t n, int p,
+k_quad_partial(const double* __restrict__ b, int64_t ldb, int64_t n, int p,
                const double* __restrict__ res, double* __restrict__ part) {
   __shared__ double smu[128];
   __shared__ double shi[FIN_THREADS], slo[FIN_THREADS];
@@ -163,7 +163,7 @@ k_quad_partial(const double* __restrict__ a, int64_t lda, int64_t n_pad, int64_t
   if (j1 > n) j1 = n;
   double hi = 0.0, lo = 0.0;
   for (int64_t j = j0 + tid; j < j1; j += FIN_THREADS) {
-    const double* zc = a + n_pad + j * lda;
+    const double* zc = b + j * ldb;
     double r = zc[p];
     for (int c = 0; c < p; ++c) r = fma(-zc[c], smu[c], r);
     dd_fma_acc(hi, lo, r, r);
@@ -193,11 +193,11 @@ __global__ void k_assemble(const double* __restrict__ part, int blocks, int64_t 
   res[VC_RES_N2LL] = (res[VC_RES_INFO] != 0.0) ? nan("") : v;
 }
 
-__global__ void k_gather_whitened(const double* __restrict__ a, int64_t lda, int64_t n_pad, int64_t n,
+__global__ void k_gather_whitened(const double* __restrict__ b, int64_t ldb, int64_t n,
                                   int p, double* __restrict__ z) {
   const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
-  for (int c = 0; c <= p; ++c) z[j + (int64_t)c * n] = a[n_pad + c + j * lda];
+  for (int c = 0; c <= p; ++c) z[j + (int64_t)c * n] = b[c + j * ldb];
 }
 
 // R = L^T as base::chol returns it: upper triangular n x n, zeros below the diagonal
@@ -235,17 +235,17 @@ void vc_launch_finalize(const VcMatrix& M, int p, int mu_mode, const double* mu_
     VC_CUDA_TRY(cudaFuncSetAttribute(k_solve_mu, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr = true;
   }
-  k_gram_partial<<<fw.blocks, FIN_THREADS, sm1, st>>>(M.a, M.lda, M.n_pad, M.n, p, fw.gram_part);
+  k_gram_partial<<<fw.blocks, FIN_THREADS, sm1, st>>>(M.b, M.ldb, M.n, p, fw.gram_part);
   k_solve_mu<<<1, FIN_THREADS, sm2, st>>>(fw.gram_part, fw.blocks, p, mu_mode, mu_in_dev, logdet_part,
                                           M.nt, info, result_dev, nullptr);
-  k_quad_partial<<<fw.blocks, FIN_THREADS, 0, st>>>(M.a, M.lda, M.n_pad, M.n, p, result_dev, fw.quad_part);
+  k_quad_partial<<<fw.blocks, FIN_THREADS, 0, st>>>(M.b, M.ldb, M.n, p, result_dev, fw.quad_part);
   k_assemble<<<1, 1, 0, st>>>(fw.quad_part, fw.blocks, M.n, result_dev);
   *launches += 4;
 }
 
 void vc_launch_gather_whitened(const VcMatrix& M, int p, double* z_out_dev, cudaStream_t st,
                                int64_t* launches) {
-  k_gather_whitened<<<(unsigned)((M.n + 255) / 256), 256, 0, st>>>(M.a, M.lda, M.n_pad, M.n, p, z_out_dev);
+  k_gather_whitened<<<(unsigned)((M.n + 255) / 256), 256, 0, st>>>(M.b, M.ldb, M.n, p, z_out_dev);
   ++*launches;
 }
 

@@ -50,7 +50,7 @@ class SVCObjective:
 
     def __init__(self, y, X, locs, W=None, cov_name="exp", tapering=None, dist=None,
                  profileLik=False, mean_est=None, pc_prior=None, device=0, nb_outer=0,
-                 lookahead=True, _dist_grid=None):
+                 lookahead=True, legacy_syrk=False, _dist_grid=None):
         self._h = C.c_void_p()
         self.y = as_f64(y).ravel()
         self.X = as_f64(X, 2)
@@ -85,7 +85,7 @@ class SVCObjective:
             cfg.taper_range = float(tapering)
         cfg.device = int(device)
         cfg.nb_outer = int(nb_outer)
-        cfg.flags = 0 if lookahead else _lib.VC_FLAG_NO_LOOKAHEAD
+        cfg.flags = (0 if lookahead else _lib.VC_FLAG_NO_LOOKAHEAD) | (_lib.VC_FLAG_LEGACY_SYRK if legacy_syrk else 0)
         self._cfg = cfg
         if _dist_grid is None:
             code = lib().vc_create(C.byref(self._h), C.byref(cfg), n, self.d, self.p, self.q,
