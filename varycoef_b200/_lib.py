@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libvarycoef_b200.so")
+LIB_PATH = os.environ.get("VC_LIB_PATH") or os.path.join(HERE, "libvarycoef_b200.so")
 
 VC_OK, VC_ERR_NOT_PD, VC_ERR_INVALID, VC_ERR_CUDA, VC_ERR_OOM = 0, 1, 2, 3, 4
 COV_IDS = {"exp": 0, "mat32": 1, "mat52": 2, "sph": 3, "wend1": 4, "wend2": 5}

@@ -103,7 +103,6 @@ struct GemmArgs {
   int n_main;           // TRSM: number of main row tiles handled (0 in solve sweeps)
   const int* tiles;     // update: packed (I | J << 16)
   int ntiles;
-  int dbg;              // debug switches (VC_DEBUG env)
 };
 
 // pointer to element (0, col) of row tile I, and its leading dimension
@@ -275,7 +274,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_syrk_ws(GemmArgs p) {
       const double* src = row_tile_ptr(p, opnd == 0 ? I : J, p.k0 + col, ldsrc);
       // pull the NEXT tile's C into L2 while this tile computes (its loads then hit L2)
       const int tn = t + gridDim.x;
-      if (tn < p.ntiles && !(p.dbg & 1)) {
+      if (tn < p.ntiles) {
         const int pk = p.tiles[tn];
         int64_t ldn;
         const double* cn = row_tile_ptr(p, pk & 0xffff, (int64_t)(pk >> 16) * TILE, ldn);
@@ -319,7 +318,11 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_syrk_ws(GemmArgs p) {
         __syncwarp();   // lanes may leave the polling loop in different iterations; mma.sync needs convergence
         const double* sa = smem + slot * STAGE_DOUBLES;
         warp_stage(sa + wm * 64 + g, sa + KC * SLD + wn * 32 + g, tig, acc);
-        if (p.dbg & 2) asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+        // Order this warp's generic-proxy reads of the slot (the LDS above) before the
+        // async-proxy refill the arrive allows.  Without the fence ptxas hoists the arrive right
+        // behind the ISSUE of the last LDS and the TMA engine can overwrite data still being read
+        // (observed: nondeterministic ~1e-5 errors; see tests: ..._bitwise_equals_per_tile_kernel).
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
         __syncwarp();
         if (lane == 0) mbar_arrive(empty + slot);
       }
@@ -512,15 +515,8 @@ void vc_chol_free_plans(VcCholWork& w) {
   w.plan_solve = VcCholPlan();
 }
 
-static int vc_debug_flags() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("VC_DEBUG"); v = e ? atoi(e) : 0; }
-  return v;
-}
-
 static GemmArgs base_args(const VcMatrix& M) {
   GemmArgs g{};
-  g.dbg = vc_debug_flags();
   g.a = M.a; g.lda = M.lda; g.b = M.b; g.ldb = M.ldb; g.nt = M.nt;
   return g;
 }
