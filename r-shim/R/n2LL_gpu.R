@@ -1,0 +1,29 @@
+# Drop-in replacement of the objective inside varycoef (R-pkg/R/objective_functions.R:4-62).
+# Same formals as n2LL, so optim(fn = n2LL, ...) in MLE_computation (R-pkg/R/SVC_mle.R:145-163),
+# optimParallel (:180-199) and SVC_selection's do.call(obj.fun$obj_fun, c(list(x = x), obj.fun$args))
+# (R-pkg/R/SVC_selection.R:74-76) keep working unchanged.  The heavy closure arguments are replaced
+# by `gpu`, an external pointer created once per fit.
+
+vcb_handle <- function(y, X, locs, W, control) {
+  cov_id   <- match(control$cov.name, c("exp", "mat32", "mat52", "sph", "wend1", "wend2")) - 1L
+  dist_id  <- match(control$dist$method, c("euclidean", "maximum", "manhattan", "minkowski")) - 1L
+  taper_id <- if (is.null(control$tapering)) 0L else
+    switch(control$cov.name, exp = 1L, mat32 = 1L, mat52 = 2L,
+           stop("tapering undefined for this covariance"))       # get_taper, utils.R:545-552
+  .Call(C_vcb_create, as.matrix(locs), as.matrix(X), as.matrix(W), as.numeric(y),
+        cov_id, dist_id, if (is.null(control$dist$p)) 2 else control$dist$p,
+        taper_id, if (is.null(control$tapering)) 0 else control$tapering, 0L)
+}
+
+n2LL <- function(x, cov_func, outer.W, y, X, W, mean.est = NULL, taper = NULL,
+                 pc.dens = NULL, Rstruct = NULL, profile = TRUE, gpu = NULL) {
+  q <- dim(W)[2]; p <- dim(X)[2]
+  mu <- if (profile) mean.est else x[1 + 2*q + 1:p]     # NULL -> GLS on the GPU
+  as.numeric(.Call(C_vcb_n2ll, gpu, x[1:(2*q+1)], mu)) + pc_penalty(x, q, pc.dens)
+}
+
+# In MLE_computation (R-pkg/R/SVC_mle.R:12-242) the edits are:
+#   - drop `d <- own_dist(...)`, `outer.W <- lapply(...)`, `taper`, `Rstruct`   (lines 33-36, 63-81)
+#   - gpu <- vcb_handle(y, X, locs, W, control)
+#   - pass `gpu = gpu` in the optim()/optimParallel() argument list and in `args` of extract_fun
+#   - med_dist: median of the pairwise distances still needed for default bounds (host, once)
