@@ -68,6 +68,7 @@ typedef struct vc_config {
 } vc_config;
 
 #define VC_FLAG_NO_LOOKAHEAD 1 /* serialise panel factorisation and trailing update (debug) */
+#define VC_FLAG_LEGACY_POTRF 4 /* unblocked diagonal-tile factorisation kernel (A/B) */
 #define VC_FLAG_LEGACY_SYRK 2  /* one-CTA-per-tile cp.async update kernel instead of the persistent one (A/B) */
 
 typedef struct vc_timing {   /* device times of the LAST evaluation, milliseconds (CUDA events) */

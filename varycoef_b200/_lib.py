@@ -20,6 +20,7 @@ TAPER_IDS = {None: 0, "wend1": 1, "wend2": 2}
 VC_MU_GLS, VC_MU_FIXED = 0, 1
 VC_FLAG_NO_LOOKAHEAD = 1
 VC_FLAG_LEGACY_SYRK = 2
+VC_FLAG_LEGACY_POTRF = 4
 
 
 class VcConfig(C.Structure):
@@ -61,7 +62,7 @@ SIGNATURES = {
     "vc_get_chol": (C.c_int, [C.c_void_p, _dp]),
     "vc_get_whitened": (C.c_int, [C.c_void_p, _dp]),
     "vc_gls_chol": (C.c_int, [C.c_int32, C.c_int64, C.c_int32, _dp, _dp, _dp, _dp]),
-    "vc_post": (C.c_int, [C.c_void_p, _dp, _dp, _dp, _dp]),
+    "vc_post": (C.c_int, [C.c_void_p, _dp, _dp, _dp, C.POINTER(C.c_double)]),
     "vc_predict": (C.c_int, [C.c_void_p, _dp, _dp, C.c_int64, _dp, _dp, _dp, _dp, _dp, _dp]),
     "vc_timings": (C.c_int, [C.c_void_p, C.POINTER(VcTiming)]),
     "vc_last_info": (C.c_int, [C.c_void_p]),

@@ -59,7 +59,7 @@ void vc_free_handle(vc_handle* h) {
   cudaSetDevice(h->device);
   if (h->dist) vc_dist_destroy(h);
   cudaFree(h->M.a); cudaFree(h->M.b); vc_chol_free_plans(h->cw); cudaFree(h->locs); cudaFree(h->x); cudaFree(h->w); cudaFree(h->y);
-  cudaFree(h->mu_in); cudaFree(h->results);
+  cudaFree(h->mu_in); cudaFree(h->results); cudaFree(h->gram_dev);
   if (h->results_host) cudaFreeHost(h->results_host);
   cudaFree(h->cw.linv); cudaFree(h->cw.logdet_part); cudaFree(h->cw.info);
   cudaFree(h->fw.gram_part); cudaFree(h->fw.quad_part);
@@ -119,6 +119,7 @@ vc_handle* vc_alloc_common(const vc_config* cfg, int64_t n, int d, int p, int q,
     h->M.nbt = 1;
     h->M.ldb = VC_BORDER_ROWS;
     h->cw.legacy_syrk = (cfg->flags & VC_FLAG_LEGACY_SYRK) != 0;
+    h->cw.legacy_potrf = (cfg->flags & VC_FLAG_LEGACY_POTRF) != 0;
     {
       cudaDeviceProp prop;
       VC_CUDA_TRY(cudaGetDeviceProperties(&prop, h->device));
@@ -141,6 +142,7 @@ vc_handle* vc_alloc_common(const vc_config* cfg, int64_t n, int d, int p, int q,
     const int m = p + 1;
     VC_CUDA_TRY(cudaMalloc(&h->fw.gram_part, (size_t)blocks * m * (m + 1) * sizeof(double)));
     VC_CUDA_TRY(cudaMalloc(&h->fw.quad_part, (size_t)blocks * 2 * sizeof(double)));
+    VC_CUDA_TRY(cudaMalloc(&h->gram_dev, (size_t)m * m * sizeof(double)));
     vc_build_init();
     vc_chol_init();
     VC_CUDA_TRY(cudaStreamSynchronize(h->st_main));
@@ -184,6 +186,7 @@ extern "C" int vc_set_data(vc_handle* h, const double* locs, const double* X, co
     if (W) upload_padded(h->w, W, h->n, h->n_pad, h->q, h->st_main);
     if (y) upload_padded(h->y, y, h->n, h->n_pad, 1, h->st_main);
     h->factor_valid = false;
+    h->factor_theta.clear();
   } catch (const VcError& e) {
     return vc_fail(h, e.code, e.msg);
   }
@@ -210,17 +213,30 @@ int vc_make_theta(const vc_handle* h, const double* theta, VcTheta* t) {
   return VC_OK;
 }
 
-// enqueue one evaluation on the handle's streams; result record `slot`
-static void enqueue_eval(vc_handle* h, const VcTheta& th, int mu_mode, int slot, bool timed) {
+// enqueue one evaluation on the handle's streams; result record `slot`.  When theta equals the
+// theta of the factor already resident (optim's probes of the mean parameters in the non-profile
+// objective, vc_post after a fit), only the O(n p) finalize runs.
+static void enqueue_eval(vc_handle* h, const VcTheta& th, const double* theta, int mu_mode, int slot,
+                         bool timed) {
   cudaStream_t st = h->st_main;
+  const size_t nth = (size_t)2 * h->q + 1;
+  const bool cached = h->factor_theta.size() == nth &&
+                      memcmp(h->factor_theta.data(), theta, nth * sizeof(double)) == 0;
   if (timed) VC_CUDA_TRY(cudaEventRecord(h->ev[0], st));
-  vc_launch_build(h->M, th, h->d, h->locs, h->w, st, &h->launches);
-  vc_launch_border(h->M, h->p, h->x, h->y, st, &h->launches);
+  if (!cached) {
+    vc_launch_build(h->M, th, h->d, h->locs, h->w, st, &h->launches);
+    vc_launch_border(h->M, h->p, h->x, h->y, st, &h->launches);
+  }
   if (timed) VC_CUDA_TRY(cudaEventRecord(h->ev[1], st));
-  vc_chol_factor(h->M, h->cw, &h->launches);
+  if (!cached) {
+    h->M.nbt = 1;
+    vc_chol_factor(h->M, h->cw, &h->launches);
+    h->factor_theta.assign(theta, theta + nth);
+  }
   if (timed) VC_CUDA_TRY(cudaEventRecord(h->ev[2], st));
   vc_launch_finalize(h->M, h->p, mu_mode, h->mu_in + (size_t)slot * 128, h->cw.logdet_part,
-                     h->cw.info, h->fw, h->results + (size_t)slot * VC_RES_STRIDE, st, &h->launches);
+                     h->cw.info, h->fw, h->results + (size_t)slot * VC_RES_STRIDE, st, &h->launches,
+                     h->gram_dev);
   if (timed) VC_CUDA_TRY(cudaEventRecord(h->ev[3], st));
 }
 
@@ -257,7 +273,7 @@ extern "C" int vc_n2ll_batch(vc_handle* h, int32_t m, const double* thetas, int3
         status[e] = VC_ERR_INVALID;
         continue;
       }
-      enqueue_eval(h, th, mu_mode, e, e == m - 1);
+      enqueue_eval(h, th, thetas + (size_t)e * nth, mu_mode, e, e == m - 1);
     }
     VC_CUDA_TRY(cudaMemcpyAsync(h->results_host, h->results, (size_t)m * VC_RES_STRIDE * sizeof(double),
                                 cudaMemcpyDeviceToHost, h->st_main));
@@ -293,6 +309,8 @@ extern "C" int vc_n2ll_batch(vc_handle* h, int32_t m, const double* thetas, int3
       h->err = "theta does not define a covariance (range <= 0 or non-finite value)";
     }
   } catch (const VcError& e) {
+    h->factor_theta.clear();
+    h->factor_valid = false;
     return vc_fail(h, e.code, e.msg);
   }
   return first;

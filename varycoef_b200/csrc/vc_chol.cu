@@ -424,6 +424,222 @@ k_potrf128(double* __restrict__ At, int64_t lda, int jt, double* __restrict__ li
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// k_potrf128b: blocked version of the diagonal-tile factorisation (default).  The 128x128 tile is
+// treated as 8x8 blocks of 16x16.  Per block column: warp 0 factors the 16x16 diagonal block and
+// inverts it in registers (shuffles); all warps solve the 16-wide panel below (DMMA, multiply by
+// the block inverse) and apply the rank-16 update to the trailing lower triangle (DMMA on 8x8
+// sub-tiles).  The full inverse is then assembled block sub-diagonal by block sub-diagonal:
+//   X_ij = -X_ii * sum_{k=j}^{i-1} L_ik X_kj      (all 16x16x16 DMMA products, one warp per block)
+// Shared array M: 129 columns x 132 doubles (column stride 132: conflict-free m8n8k4 fragments)
+//   L(i, j) (i >= j) at M[j*PLD + i];   X(i, c) = Linv(i, c) (i >= c) at M[(i+1)*PLD + c].
+// ---------------------------------------------------------------------------------------------
+constexpr int PLD = 132;
+constexpr int PB = 16;
+constexpr int SS_LD = 20;   // per-warp 16x16 scratch, column stride 20 doubles
+constexpr int POTRFB_SMEM = ((TILE + 1) * PLD + TILE + 8 * PB * SS_LD) * (int)sizeof(double);
+
+__device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+
+__global__ void __launch_bounds__(POTRF_THREADS, 1)
+k_potrf128b(double* __restrict__ At, int64_t lda, int jt, double* __restrict__ linv_all,
+            double* __restrict__ logdet_part, int* __restrict__ info) {
+  extern __shared__ __align__(16) double M[];
+  double* sdiag = M + (TILE + 1) * PLD;
+  double* scratch = sdiag + TILE;
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, tig = lane & 3;
+
+  for (int idx = tid; idx < TILE * TILE; idx += POTRF_THREADS) {
+    const int r = idx & (TILE - 1), c = idx >> 7;
+    if (r >= c) M[c * PLD + r] = At[r + (int64_t)c * lda];
+  }
+  __syncthreads();
+
+  for (int kb = 0; kb < TILE / PB; ++kb) {
+    const int k0 = kb * PB;
+    // ---- A: diagonal 16x16 block, factor + inverse, warp 0, lane r < 16 owns row r ----
+    if (warp == 0) {
+      const int r = lane & 15;
+      double a[PB], x[PB];
+#pragma unroll
+      for (int k = 0; k < PB; ++k) a[k] = (k <= r) ? M[(k0 + k) * PLD + k0 + r] : 0.0;
+#pragma unroll
+      for (int j = 0; j < PB; ++j) {
+        const double ajj = shfl_d(a[j], j);
+        const double d = sqrt(ajj);
+        if (lane == j) {
+          sdiag[k0 + j] = d;
+          if (!(ajj > 0.0)) atomicMin(info, jt * TILE + k0 + j + 1);
+        }
+        const double dinv = 1.0 / d;
+        if (r == j) a[j] = d;
+        else if (r > j) a[j] *= dinv;
+#pragma unroll
+        for (int k = j + 1; k < PB; ++k) {
+          const double lkj = shfl_d(a[j], k);
+          if (r >= k) a[k] = fma(-a[j], lkj, a[k]);
+        }
+      }
+      // inverse: lane c builds column c of D^-1 by forward substitution
+      const int c = r;
+#pragma unroll
+      for (int i = 0; i < PB; ++i) {
+        double sacc = (i == c) ? 1.0 : 0.0;
+#pragma unroll
+        for (int k = 0; k < i; ++k) {
+          const double dik = shfl_d(a[k], i);
+          if (k >= c) sacc = fma(-dik, x[k], sacc);
+        }
+        const double dii = shfl_d(a[i], i);
+        x[i] = (i >= c) ? sacc / dii : 0.0;
+      }
+      if (lane < PB) {
+#pragma unroll
+        for (int k = 0; k < PB; ++k)
+          if (k <= r) M[(k0 + k) * PLD + k0 + r] = a[k];
+#pragma unroll
+        for (int i = 0; i < PB; ++i)
+          if (i >= c) M[(k0 + i + 1) * PLD + k0 + c] = x[i];
+      }
+    }
+    __syncthreads();
+    const int nsub = (TILE - k0 - PB) / 8;   // 8-row sub-tiles below the diagonal block
+    // ---- B: panel solve  P = A * Dinv^T  on rows [k0+16, 128) ----
+    for (int ms = warp; ms < nsub; ms += 8) {
+      const int row0 = k0 + PB + 8 * ms;
+      double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+#pragma unroll
+      for (int k4 = 0; k4 < 4; ++k4) {
+        const int k = 4 * k4 + tig;
+        const double af = M[(k0 + k) * PLD + row0 + g];
+#pragma unroll
+        for (int nn = 0; nn < 2; ++nn) {
+          const int c = 8 * nn + g;
+          const double bf = (k <= c) ? M[(k0 + c + 1) * PLD + k0 + k] : 0.0;
+          dmma884(acc[nn][0], acc[nn][1], af, bf);
+        }
+      }
+      __syncwarp();
+#pragma unroll
+      for (int nn = 0; nn < 2; ++nn) {
+        M[(k0 + 8 * nn + 2 * tig) * PLD + row0 + g] = acc[nn][0];
+        M[(k0 + 8 * nn + 2 * tig + 1) * PLD + row0 + g] = acc[nn][1];
+      }
+    }
+    __syncthreads();
+    // ---- C: trailing update on the lower triangle of 8x8 sub-tiles ----
+    const int npair = nsub * (nsub + 1) / 2;
+    for (int t = warp; t < npair; t += 8) {
+      int sa = (int)((sqrtf(8.0f * t + 1.0f) - 1.0f) * 0.5f);
+      while ((sa + 1) * (sa + 2) / 2 <= t) ++sa;
+      while (sa * (sa + 1) / 2 > t) --sa;
+      const int sb = t - sa * (sa + 1) / 2;
+      const int rowA = k0 + PB + 8 * sa, rowB = k0 + PB + 8 * sb;
+      double c0 = M[(rowB + 2 * tig) * PLD + rowA + g];
+      double c1 = M[(rowB + 2 * tig + 1) * PLD + rowA + g];
+#pragma unroll
+      for (int k4 = 0; k4 < 4; ++k4) {
+        const int k = k0 + 4 * k4 + tig;
+        dmma884(c0, c1, -M[k * PLD + rowA + g], M[k * PLD + rowB + g]);
+      }
+      if (sa != sb || g >= 2 * tig) M[(rowB + 2 * tig) * PLD + rowA + g] = c0;
+      if (sa != sb || g >= 2 * tig + 1) M[(rowB + 2 * tig + 1) * PLD + rowA + g] = c1;
+    }
+    __syncthreads();
+  }
+
+  // ---- inverse, block sub-diagonal d = 1..7: X_ij = -X_ii * sum_k L_ik X_kj ----
+  double* ss = scratch + warp * PB * SS_LD;
+  for (int d = 1; d < TILE / PB; ++d) {
+    const int bi = d + warp, bj = warp;
+    if (bi < TILE / PB) {
+      double s[2][2][2];
+#pragma unroll
+      for (int mm = 0; mm < 2; ++mm)
+#pragma unroll
+        for (int nn = 0; nn < 2; ++nn) s[mm][nn][0] = s[mm][nn][1] = 0.0;
+      for (int kbk = bj; kbk < bi; ++kbk) {
+#pragma unroll
+        for (int k4 = 0; k4 < 4; ++k4) {
+          const int kk = 4 * k4 + tig;             // within block kbk
+          double af[2], bf[2];
+#pragma unroll
+          for (int mm = 0; mm < 2; ++mm) af[mm] = M[(PB * kbk + kk) * PLD + PB * bi + 8 * mm + g];
+#pragma unroll
+          for (int nn = 0; nn < 2; ++nn) {
+            const int n = 8 * nn + g;
+            // X_kj(kk, n); the diagonal block (kbk == bj) is lower triangular, its upper part is not stored
+            bf[nn] = (kbk > bj || kk >= n) ? M[(PB * kbk + kk + 1) * PLD + PB * bj + n] : 0.0;
+          }
+#pragma unroll
+          for (int mm = 0; mm < 2; ++mm)
+#pragma unroll
+            for (int nn = 0; nn < 2; ++nn) dmma884(s[mm][nn][0], s[mm][nn][1], af[mm], bf[nn]);
+        }
+      }
+      // S -> per-warp scratch as S(kk, n) at ss[n * SS_LD + kk]
+#pragma unroll
+      for (int mm = 0; mm < 2; ++mm)
+#pragma unroll
+        for (int nn = 0; nn < 2; ++nn) {
+          ss[(8 * nn + 2 * tig) * SS_LD + 8 * mm + g] = s[mm][nn][0];
+          ss[(8 * nn + 2 * tig + 1) * SS_LD + 8 * mm + g] = s[mm][nn][1];
+        }
+      __syncwarp();
+      double xo[2][2][2];
+#pragma unroll
+      for (int mm = 0; mm < 2; ++mm)
+#pragma unroll
+        for (int nn = 0; nn < 2; ++nn) xo[mm][nn][0] = xo[mm][nn][1] = 0.0;
+#pragma unroll
+      for (int k4 = 0; k4 < 4; ++k4) {
+        const int kk = 4 * k4 + tig;
+        double af[2], bf[2];
+#pragma unroll
+        for (int mm = 0; mm < 2; ++mm) {
+          const int r = 8 * mm + g;                // -X_ii(r, kk), lower triangular
+          af[mm] = (kk <= r) ? -M[(PB * bi + r + 1) * PLD + PB * bi + kk] : 0.0;
+        }
+#pragma unroll
+        for (int nn = 0; nn < 2; ++nn) bf[nn] = ss[(8 * nn + g) * SS_LD + kk];
+#pragma unroll
+        for (int mm = 0; mm < 2; ++mm)
+#pragma unroll
+          for (int nn = 0; nn < 2; ++nn) dmma884(xo[mm][nn][0], xo[mm][nn][1], af[mm], bf[nn]);
+      }
+      // X_ij(r, c) -> M[(16 bi + r + 1) * PLD + 16 bj + c]
+#pragma unroll
+      for (int mm = 0; mm < 2; ++mm)
+#pragma unroll
+        for (int nn = 0; nn < 2; ++nn) {
+          double* dst = M + (PB * bi + 8 * mm + g + 1) * PLD + PB * bj + 8 * nn + 2 * tig;
+          dst[0] = xo[mm][nn][0];
+          dst[1] = xo[mm][nn][1];
+        }
+    }
+    __syncthreads();
+  }
+
+  // ---- write back ----
+  double* linv = linv_all + (int64_t)jt * TILE * TILE;
+  for (int idx = tid; idx < TILE * TILE; idx += POTRF_THREADS) {
+    const int r = idx & (TILE - 1), c = idx >> 7;
+    if (r >= c) At[r + (int64_t)c * lda] = M[c * PLD + r];
+    linv[idx] = (r >= c) ? M[(r + 1) * PLD + c] : 0.0;
+  }
+  if (tid < 32) {
+    double sl = 0.0;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) sl += log(sdiag[lane * 4 + a]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sl += __shfl_xor_sync(0xffffffffu, sl, o);
+    if (lane == 0) logdet_part[jt] = sl;
+  }
+}
+
 __global__ void k_reset_info(int* info) { *info = INT_MAX; }
 
 // ---- host: tile lists -------------------------------------------------------------------------
@@ -505,6 +721,7 @@ void vc_chol_init() {
   VC_CUDA_TRY(cudaFuncSetAttribute(k_syrk_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
   VC_CUDA_TRY(cudaFuncSetAttribute(k_syrk_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM));
   VC_CUDA_TRY(cudaFuncSetAttribute(k_potrf128, cudaFuncAttributeMaxDynamicSharedMemorySize, POTRF_SMEM));
+  VC_CUDA_TRY(cudaFuncSetAttribute(k_potrf128b, cudaFuncAttributeMaxDynamicSharedMemorySize, POTRFB_SMEM));
   done = true;
 }
 
@@ -584,7 +801,10 @@ void vc_chol_factor(const VcMatrix& M, VcCholWork& w, int64_t* launches, int mod
     for (int jt = ob; jt < oe; ++jt) {
       if (!solve) {
         double* diag = M.a + (int64_t)jt * TILE * (M.lda + 1);
-        k_potrf128<<<1, POTRF_THREADS, POTRF_SMEM, sp>>>(diag, M.lda, jt, w.linv, w.logdet_part, w.info);
+        if (w.legacy_potrf)
+          k_potrf128<<<1, POTRF_THREADS, POTRF_SMEM, sp>>>(diag, M.lda, jt, w.linv, w.logdet_part, w.info);
+        else
+          k_potrf128b<<<1, POTRF_THREADS, POTRFB_SMEM, sp>>>(diag, M.lda, jt, w.linv, w.logdet_part, w.info);
         ++*launches;
       }
       GemmArgs g = base_args(M);

@@ -93,6 +93,7 @@ struct VcCholWork {
   int nb_tiles;          // outer block in tiles (nb_outer / 128)
   bool lookahead;
   bool legacy_syrk;      // use the non-persistent cp.async SYRK kernel (A/B testing)
+  bool legacy_potrf;     // use the unblocked diagonal-tile kernel (A/B testing)
   int num_sms;
   cudaStream_t st_main, st_panel;
   cudaEvent_t ev_panel, ev_update, ev_col;
@@ -112,7 +113,8 @@ struct VcFinalWork {
 };
 void vc_launch_finalize(const VcMatrix& M, int p, int mu_mode, const double* mu_in_dev,
                         const double* logdet_part, const int* info, VcFinalWork& fw,
-                        double* result_dev, cudaStream_t st, int64_t* launches);
+                        double* result_dev, cudaStream_t st, int64_t* launches,
+                        double* gram_out_dev = nullptr);
 void vc_launch_gather_whitened(const VcMatrix& M, int p, double* z_out_dev, cudaStream_t st,
                                int64_t* launches);
 void vc_launch_extract_chol(const VcMatrix& M, double* r_out_dev, cudaStream_t st,

@@ -221,7 +221,7 @@ __global__ void k_extract_chol(const double* __restrict__ a, int64_t lda, int64_
 
 void vc_launch_finalize(const VcMatrix& M, int p, int mu_mode, const double* mu_in_dev,
                         const double* logdet_part, const int* info, VcFinalWork& fw,
-                        double* result_dev, cudaStream_t st, int64_t* launches) {
+                        double* result_dev, cudaStream_t st, int64_t* launches, double* gram_out_dev) {
   const int m = p + 1;
   const int npairs = m * (m + 1) / 2;
   const size_t sm1 = ((size_t)m * CHUNK + 2 * (size_t)npairs) * sizeof(double);
@@ -237,7 +237,7 @@ void vc_launch_finalize(const VcMatrix& M, int p, int mu_mode, const double* mu_
   }
   k_gram_partial<<<fw.blocks, FIN_THREADS, sm1, st>>>(M.b, M.ldb, M.n, p, fw.gram_part);
   k_solve_mu<<<1, FIN_THREADS, sm2, st>>>(fw.gram_part, fw.blocks, p, mu_mode, mu_in_dev, logdet_part,
-                                          M.nt, info, result_dev, nullptr);
+                                          M.nt, info, result_dev, gram_out_dev);
   k_quad_partial<<<fw.blocks, FIN_THREADS, 0, st>>>(M.b, M.ldb, M.n, p, result_dev, fw.quad_part);
   k_assemble<<<1, 1, 0, st>>>(fw.quad_part, fw.blocks, M.n, result_dev);
   *launches += 4;

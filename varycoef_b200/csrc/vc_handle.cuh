@@ -21,6 +21,8 @@ struct vc_handle {
   vc_timing last_timing{};
   int last_info = 0;
   bool factor_valid = false;
+  std::vector<double> factor_theta;  // theta of the factor resident in M (empty = none)
+  double* gram_dev = nullptr;        // (p+1)^2 Gram of the whitened [X y] of the last evaluation
   int64_t launches = 0;
   std::string err;
   // distributed state lives in vc_dist.cu

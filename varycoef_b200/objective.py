@@ -50,7 +50,7 @@ class SVCObjective:
 
     def __init__(self, y, X, locs, W=None, cov_name="exp", tapering=None, dist=None,
                  profileLik=False, mean_est=None, pc_prior=None, device=0, nb_outer=0,
-                 lookahead=True, legacy_syrk=False, _dist_grid=None):
+                 lookahead=True, legacy_syrk=False, legacy_potrf=False, _dist_grid=None):
         self._h = C.c_void_p()
         self.y = as_f64(y).ravel()
         self.X = as_f64(X, 2)
@@ -85,7 +85,7 @@ class SVCObjective:
             cfg.taper_range = float(tapering)
         cfg.device = int(device)
         cfg.nb_outer = int(nb_outer)
-        cfg.flags = (0 if lookahead else _lib.VC_FLAG_NO_LOOKAHEAD) | (_lib.VC_FLAG_LEGACY_SYRK if legacy_syrk else 0)
+        cfg.flags = (0 if lookahead else _lib.VC_FLAG_NO_LOOKAHEAD) | (_lib.VC_FLAG_LEGACY_SYRK if legacy_syrk else 0) | (_lib.VC_FLAG_LEGACY_POTRF if legacy_potrf else 0)
         self._cfg = cfg
         if _dist_grid is None:
             code = lib().vc_create(C.byref(self._h), C.byref(cfg), n, self.d, self.p, self.q,
@@ -239,14 +239,14 @@ class SVCObjective:
     def padded_n(self):
         return int(lib().vc_padded_n(self._h))
 
-    def post(self, x):
+    def post(self, x, edof=True):
         """prep_par_output / eff_dof pieces (utils.R:423-473, eff_dof.R:7-21) from the GPU factor."""
         theta = np.ascontiguousarray(np.asarray(x, dtype=np.float64).ravel()[:2 * self.q + 1])
         mu = np.empty(self.p)
         sfe = np.empty((self.p, self.p), order="F")
-        edof = C.c_double()
-        check(lib().vc_post(self._h, ptr(theta), ptr(mu), ptr(sfe), C.byref(edof)), self._h)
-        return {"mu_gls": mu, "Sigma_FE": sfe, "edof": edof.value}
+        ed = C.c_double(float("nan"))
+        check(lib().vc_post(self._h, ptr(theta), ptr(mu), ptr(sfe), C.byref(ed) if edof else None), self._h)
+        return {"mu_gls": mu, "Sigma_FE": sfe, "edof": ed.value}
 
     def predict(self, x, mu, newlocs=None, newX=None, newW=None, compute_y_var=False):
         """predict.SVC_mle (predict-SVC_mle.R:80-267) on the GPU."""

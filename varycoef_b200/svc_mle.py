@@ -203,7 +203,7 @@ def prep_par_output(output_par, obj, profileLik, H, q):
     output_par = np.asarray(output_par, dtype=np.float64)
     post = None
     if profileLik:
-        post = obj.post(output_par[:2 * q + 1])
+        post = obj.post(output_par[:2 * q + 1], edof=False)
         mu = post["mu_gls"]
     else:
         mu = output_par[2 * q + 1:2 * q + 1 + p]
