@@ -176,6 +176,10 @@ VC_API int vc_create_dist(vc_handle** h, const vc_config* cfg, int64_t n, int32_
 VC_API int vc_bc_owner(int32_t bi, int32_t bj, int32_t pr, int32_t pc);
 VC_API int vc_bc_local(int32_t b, int32_t nprocs_dim);
 VC_API int vc_bc_count(int32_t nblocks, int32_t coord, int32_t nprocs_dim);
+/* trailing-update tiles (packed I | J << 16, global 128-tile indices) owned by `rank` after the outer block
+ * ending at tile `oe`: J in [oe, nt), I in [J, nt + nbt); returns the count, fills out[0..cap) if non-NULL */
+VC_API int vc_bc_trailing_tiles(int32_t nt, int32_t nbt, int32_t nb, int32_t pr, int32_t pc, int32_t rank,
+                         int32_t oe, int32_t* out, int32_t cap);
 
 #ifdef __cplusplus
 }

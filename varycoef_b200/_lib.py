@@ -79,6 +79,7 @@ SIGNATURES = {
     "vc_bc_owner": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "vc_bc_local": (C.c_int, [C.c_int32, C.c_int32]),
     "vc_bc_count": (C.c_int, [C.c_int32, C.c_int32, C.c_int32]),
+    "vc_bc_trailing_tiles": (C.c_int, [C.c_int32] * 7 + [C.POINTER(C.c_int32), C.c_int32]),
 }
 
 

@@ -31,6 +31,8 @@ struct BuildArgs {
   int d;
   const double* locs;   // n_pad x d
   const double* w;      // n_pad x q
+  const int* tiles;     // optional list of packed (I | J << 16) global tiles (distributed build)
+  int blk, pr, pc;      // block-cyclic distribution of the OUTPUT (0 = plain)
   VcTheta th;
 };
 
@@ -46,7 +48,11 @@ __global__ void __launch_bounds__(BUILD_THREADS) k_build(BuildArgs p) {
   double* rowA = rowX + d * TILE;
 
   int I, J;
-  if (FULL) {
+  if (p.tiles) {
+    const int packed = p.tiles[blockIdx.x];
+    I = packed & 0xffff;
+    J = packed >> 16;
+  } else if (FULL) {
     I = blockIdx.x % p.nt;
     J = blockIdx.x / p.nt;
   } else {
@@ -74,6 +80,10 @@ __global__ void __launch_bounds__(BUILD_THREADS) k_build(BuildArgs p) {
   const int rg = tid & 63, cg = tid >> 6;
   const int r0 = 2 * rg;
   const int64_t gi0 = (int64_t)I * TILE + r0;
+  // position in the (possibly block-cyclic local) output
+  const int lI = p.blk ? ((I / p.blk) / p.pr) * p.blk + I % p.blk : I;
+  const int lJ = p.blk ? ((J / p.blk) / p.pc) * p.blk + J % p.blk : J;
+  const int64_t oi0 = (int64_t)lI * TILE + r0, oj0 = (int64_t)lJ * TILE;
   const int method = p.th.dist_method;
   const double mink = p.th.mink_p;
 
@@ -147,17 +157,18 @@ __global__ void __launch_bounds__(BUILD_THREADS) k_build(BuildArgs p) {
         if (gi0 + 1 < p.n) p.out[gi0 + 1 + gj * p.ld] = v1;
       }
     } else {
-      *reinterpret_cast<double2*>(p.out + gi0 + gj * p.ld) = make_double2(v0, v1);
+      *reinterpret_cast<double2*>(p.out + oi0 + (oj0 + j) * p.ld) = make_double2(v0, v1);
     }
   }
 }
 
 template <bool FULL>
-void launch_build_t(const BuildArgs& a, cudaStream_t st) {
+void launch_build_t(const BuildArgs& a, cudaStream_t st, unsigned grid_override = 0) {
   const int d = a.d, q = a.th.q;
   const bool reg = (d <= RD && q <= RQ);
   const size_t smem = (VC_EXP_TABLE_SIZE + 2 * (size_t)(d + q) * TILE) * sizeof(double);
-  const unsigned grid = FULL ? (unsigned)a.nt * a.nt : (unsigned)((int64_t)a.nt * (a.nt + 1) / 2);
+  const unsigned grid = grid_override ? grid_override
+                        : FULL ? (unsigned)a.nt * a.nt : (unsigned)((int64_t)a.nt * (a.nt + 1) / 2);
 #define VC_BUILD_CASE(C)                                                               \
   case C:                                                                              \
     if (reg) k_build<C, true, FULL><<<grid, BUILD_THREADS, smem, st>>>(a);             \
@@ -204,6 +215,41 @@ void vc_launch_build(const VcMatrix& M, const VcTheta& th, int d, const double* 
   a.out = M.a; a.ld = M.lda; a.n = M.n; a.n_pad = M.n_pad; a.nt = M.nt; a.d = d;
   a.locs = locs_pad; a.w = w_pad; a.th = th;
   launch_build_t<false>(a, st);
+  ++*launches;
+}
+
+// distributed build: only the listed global tiles, written at their block-cyclic local position
+void vc_launch_build_tiles(double* a_loc, int64_t lda_loc, int64_t n, int64_t n_pad, const VcTheta& th, int d,
+                           const double* locs_pad, const double* w_pad, const int* tiles, int ntiles,
+                           int blk, int pr, int pc, cudaStream_t st, int64_t* launches) {
+  if (ntiles <= 0) return;
+  BuildArgs a{};
+  a.out = a_loc; a.ld = lda_loc; a.n = n; a.n_pad = n_pad; a.nt = (int)(n_pad / TILE); a.d = d;
+  a.locs = locs_pad; a.w = w_pad; a.th = th;
+  a.tiles = tiles; a.blk = blk; a.pr = pr; a.pc = pc;
+  launch_build_t<false>(a, st, (unsigned)ntiles);
+  ++*launches;
+}
+
+// border tile 0 of a block-cyclic column distribution: local column tile lj <-> global tile gj[lj]
+__global__ void k_border_dist(double* b, int64_t ldb, int64_t n_pad, int p, const double* __restrict__ x,
+                              const double* __restrict__ y, const int* __restrict__ col_tiles, int nloc) {
+  const int lj = blockIdx.x;
+  const int64_t gj0 = (int64_t)col_tiles[lj] * TILE;
+  for (int idx = threadIdx.x; idx < TILE * TILE; idx += blockDim.x) {
+    const int c = idx & (TILE - 1), jj = idx >> 7;
+    const int64_t j = gj0 + jj;
+    double v = 0.0;
+    if (c < p) v = x[(int64_t)c * n_pad + j];
+    else if (c == p) v = y[j];
+    b[c + ((int64_t)lj * TILE + jj) * ldb] = v;
+  }
+}
+void vc_launch_border_dist(double* b, int64_t ldb, int64_t n_pad, int p, const double* x_pad,
+                           const double* y_pad, const int* col_tiles_dev, int nloc, cudaStream_t st,
+                           int64_t* launches) {
+  if (nloc <= 0) return;
+  k_border_dist<<<nloc, 256, 0, st>>>(b, ldb, n_pad, p, x_pad, y_pad, col_tiles_dev, nloc);
   ++*launches;
 }
 

@@ -90,29 +90,33 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                : "d"(a), "d"(b));
 }
 
-struct GemmArgs {
-  double* a;            // main matrix (row tiles 0 .. nt-1)
-  int64_t lda;
-  double* b;            // border rows (row tiles nt .. nt+nbt-1)
-  int64_t ldb;
-  int nt;
-  const double* linv;   // TRSM: 128x128 inverse factor (ld 128)
-  int k0;               // first panel column (elements)
-  int K;                // panel depth (multiple of KC)
-  int jt;               // TRSM: panel tile column
-  int n_main;           // TRSM: number of main row tiles handled (0 in solve sweeps)
-  const int* tiles;     // update: packed (I | J << 16)
-  int ntiles;
-};
+using GemmArgs = VcGemmArgs;
 
-// pointer to element (0, col) of row tile I, and its leading dimension
+// local tile index of global tile t in a block-cyclic distribution over P processes
+__device__ __forceinline__ int loc_tile(const GemmArgs& p, int t, int P) {
+  return p.blk ? ((t / p.blk) / P) * p.blk + t % p.blk : t;
+}
+// pointer to element (0, col) of row tile I in the (local) matrix / border; col in LOCAL elements
 __device__ __forceinline__ double* row_tile_ptr(const GemmArgs& p, int I, int64_t col, int64_t& ld) {
   if (I < p.nt) {
     ld = p.lda;
-    return p.a + (int64_t)I * TILE + col * p.lda;
+    return p.a + (int64_t)loc_tile(p, I, p.pr) * TILE + col * p.lda;
   }
   ld = p.ldb;
   return p.b + (int64_t)(I - p.nt) * TILE + col * p.ldb;
+}
+// C tile (I, J), J a global column tile
+__device__ __forceinline__ double* c_tile_ptr(const GemmArgs& p, int I, int J, int64_t& ld) {
+  return row_tile_ptr(p, I, (int64_t)loc_tile(p, J, p.pc) * TILE, ld);
+}
+// operand row tile I, panel column kcol: from a gathered panel buffer, or from the matrix itself
+__device__ __forceinline__ const double* op_ptr(const GemmArgs& p, const VcOpSrc& s, int I, int kcol,
+                                                int64_t& ld) {
+  if (s.pnl) {
+    ld = s.ld;
+    return s.pnl + (int64_t)(I - s.tile0) * s.tile_stride + (int64_t)(s.col0 + kcol) * s.ld;
+  }
+  return row_tile_ptr(p, I, (int64_t)p.k0 + kcol, ld);
 }
 
 // one pipeline stage of a warp: 4 k4 steps of 12 fragment loads + 32 DMMA.
@@ -178,13 +182,14 @@ __device__ __forceinline__ void gemm_mainloop(const double* __restrict__ Ag, int
 // ---- panel solve: X(I, jt) = A(I, jt) * Linv^T ------------------------------------------------
 __global__ void __launch_bounds__(GEMM_THREADS, 1) k_trsm_panel(GemmArgs p) {
   extern __shared__ __align__(16) double smem[];
-  const int I = ((int)blockIdx.x < p.n_main) ? p.jt + 1 + blockIdx.x : p.nt + (blockIdx.x - p.n_main);
+  const int I = p.tiles ? (p.tiles[blockIdx.x] & 0xffff)
+                        : (((int)blockIdx.x < p.n_main) ? p.jt + 1 + blockIdx.x : p.nt + (blockIdx.x - p.n_main));
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
   const int wm = warp & 1, wn = warp >> 1;
   const int g = lane >> 2, tig = lane & 3;
   int64_t ld;
-  double* Ct = row_tile_ptr(p, I, (int64_t)p.jt * TILE, ld);
+  double* Ct = c_tile_ptr(p, I, p.jt, ld);
   double acc[8][4][2];
 #pragma unroll
   for (int i = 0; i < 8; ++i)
@@ -213,9 +218,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_syrk_tiles(GemmArgs p) {
   const int wm = warp & 1, wn = warp >> 1;
   const int g = lane >> 2, tig = lane & 3;
   int64_t ldc, ldpi, ldpj;
-  double* Ct = row_tile_ptr(p, I, (int64_t)J * TILE, ldc);
-  const double* Pi = row_tile_ptr(p, I, p.k0, ldpi);
-  const double* Pj = row_tile_ptr(p, J, p.k0, ldpj);
+  double* Ct = c_tile_ptr(p, I, J, ldc);
+  const double* Pi = op_ptr(p, p.src_a, I, 0, ldpi);
+  const double* Pj = op_ptr(p, p.src_b, J, 0, ldpj);
   double* cbase = Ct + (wm * 64 + g) + (int64_t)(wn * 32 + 2 * tig) * ldc;
   double acc[8][4][2];
   // acc starts at -C so that the epilogue is a pure store: C_new = -(-C + sum a b)
@@ -271,13 +276,13 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_syrk_ws(GemmArgs p) {
       const int packed = p.tiles[t];
       const int I = packed & 0xffff, J = packed >> 16;
       int64_t ldsrc;
-      const double* src = row_tile_ptr(p, opnd == 0 ? I : J, p.k0 + col, ldsrc);
+      const double* src = opnd == 0 ? op_ptr(p, p.src_a, I, col, ldsrc) : op_ptr(p, p.src_b, J, col, ldsrc);
       // pull the NEXT tile's C into L2 while this tile computes (its loads then hit L2)
       const int tn = t + gridDim.x;
       if (tn < p.ntiles) {
         const int pk = p.tiles[tn];
         int64_t ldn;
-        const double* cn = row_tile_ptr(p, pk & 0xffff, (int64_t)(pk >> 16) * TILE, ldn);
+        const double* cn = c_tile_ptr(p, pk & 0xffff, pk >> 16, ldn);
 #pragma unroll
         for (int c = 0; c < 4; ++c) bulk_prefetch_l2(cn + (int64_t)(lane * 4 + c) * ldn, TILE * 8);
       }
@@ -301,7 +306,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_syrk_ws(GemmArgs p) {
       const int packed = p.tiles[t];
       const int I = packed & 0xffff, J = packed >> 16;
       int64_t ldc;
-      double* Ct = row_tile_ptr(p, I, (int64_t)J * TILE, ldc);
+      double* Ct = c_tile_ptr(p, I, J, ldc);
       double* cbase = Ct + (wm * 64 + g) + (int64_t)(wn * 32 + 2 * tig) * ldc;
       double acc[8][4][2];
 #pragma unroll
@@ -640,6 +645,21 @@ k_potrf128b(double* __restrict__ At, int64_t lda, int jt, double* __restrict__ l
   }
 }
 
+// copy K panel columns (local column lcol0..) of the listed row tiles into a tile-major buffer:
+// tile I -> dst + (I - tile0) * 128 * K, column-major inside with ld 128 (distributed driver)
+__global__ void __launch_bounds__(256) k_pack_tiles(GemmArgs p, const int* __restrict__ tiles, int lcol0, int K,
+                                                    double* __restrict__ dst, int tile0) {
+  const int I = tiles[blockIdx.x] & 0xffff;
+  int64_t ld;
+  const double* src = row_tile_ptr(p, I, lcol0, ld);
+  double* d = dst + (int64_t)(I - tile0) * TILE * K;
+  for (int idx = threadIdx.x; idx < (TILE / 2) * K; idx += blockDim.x) {
+    const int r2 = idx % (TILE / 2), c = idx / (TILE / 2);
+    *reinterpret_cast<double2*>(d + (int64_t)c * TILE + 2 * r2) =
+        *reinterpret_cast<const double2*>(src + (int64_t)c * ld + 2 * r2);
+  }
+}
+
 __global__ void k_reset_info(int* info) { *info = INT_MAX; }
 
 // ---- host: tile lists -------------------------------------------------------------------------
@@ -732,6 +752,35 @@ void vc_chol_free_plans(VcCholWork& w) {
   w.plan_solve = VcCholPlan();
 }
 
+void vc_launch_potrf(double* diag, int64_t lda, int jt, double* linv_all, double* logdet_part, int* info,
+                     bool legacy, cudaStream_t st, int64_t* launches) {
+  if (legacy) k_potrf128<<<1, POTRF_THREADS, POTRF_SMEM, st>>>(diag, lda, jt, linv_all, logdet_part, info);
+  else k_potrf128b<<<1, POTRF_THREADS, POTRFB_SMEM, st>>>(diag, lda, jt, linv_all, logdet_part, info);
+  ++*launches;
+}
+void vc_launch_trsm(const VcGemmArgs& g, int grid, cudaStream_t st, int64_t* launches) {
+  if (grid <= 0) return;
+  k_trsm_panel<<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(g);
+  ++*launches;
+}
+void vc_launch_syrk(const VcGemmArgs& g, int num_sms, bool legacy, cudaStream_t st, int64_t* launches) {
+  if (g.ntiles <= 0) return;
+  if (legacy) k_syrk_tiles<<<g.ntiles, GEMM_THREADS, GEMM_SMEM, st>>>(g);
+  else k_syrk_ws<<<std::min(g.ntiles, std::max(num_sms, 1)), WS_THREADS, WS_SMEM, st>>>(g);
+  ++*launches;
+}
+void vc_launch_reset_info(int* info, cudaStream_t st, int64_t* launches) {
+  k_reset_info<<<1, 1, 0, st>>>(info);
+  ++*launches;
+}
+void vc_launch_pack_tiles(const VcGemmArgs& g, const int* tiles, int ntiles, int lcol0, int K, double* dst,
+                          int tile0, cudaStream_t st, int64_t* launches) {
+  if (ntiles <= 0) return;
+  k_pack_tiles<<<ntiles, 256, 0, st>>>(g, tiles, lcol0, K, dst, tile0);
+  ++*launches;
+}
+void vc_append_trapezoid(std::vector<int>& out, int J0, int J1, int nrows) { append_trapezoid(out, J0, J1, nrows); }
+
 static GemmArgs base_args(const VcMatrix& M) {
   GemmArgs g{};
   g.a = M.a; g.lda = M.lda; g.b = M.b; g.ldb = M.ldb; g.nt = M.nt;
@@ -744,13 +793,7 @@ static void launch_update(const VcMatrix& M, const VcCholWork& w, const VcCholPl
   if (c.ntiles == 0) return;
   GemmArgs g = base_args(M);
   g.k0 = c.k0; g.K = c.K; g.tiles = pl.tiles_dev + c.tile_off; g.ntiles = c.ntiles;
-  if (w.legacy_syrk) {
-    k_syrk_tiles<<<c.ntiles, GEMM_THREADS, GEMM_SMEM, st>>>(g);
-  } else {
-    const int grid = std::min(c.ntiles, std::max(w.num_sms - reserve_sms, 1));
-    k_syrk_ws<<<grid, WS_THREADS, WS_SMEM, st>>>(g);
-  }
-  ++*launches;
+  vc_launch_syrk(g, w.num_sms - reserve_sms, w.legacy_syrk, st, launches);
 }
 
 // A persistent update kernel keeps every SM it starts on until it is done, so the lookahead panel

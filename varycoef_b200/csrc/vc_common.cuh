@@ -72,8 +72,37 @@ void vc_launch_sigma_full(double* out, int64_t n, int64_t n_pad, const VcTheta& 
                           const double* locs_pad, const double* w_pad, cudaStream_t st,
                           int64_t* launches);
 void vc_build_init();
+void vc_launch_build_tiles(double* a_loc, int64_t lda_loc, int64_t n, int64_t n_pad, const VcTheta& th, int d,
+                           const double* locs_pad, const double* w_pad, const int* tiles, int ntiles,
+                           int blk, int pr, int pc, cudaStream_t st, int64_t* launches);
+void vc_launch_border_dist(double* b, int64_t ldb, int64_t n_pad, int p, const double* x_pad,
+                           const double* y_pad, const int* col_tiles_dev, int nloc, cudaStream_t st,
+                           int64_t* launches);
 
 // vc_chol.cu
+struct VcOpSrc {          // where a GEMM operand row tile comes from
+  const double* pnl;      // gathered panel buffer (tile-major), or nullptr = the matrix itself at column k0
+  int64_t ld;             // leading dimension inside a tile of the buffer
+  int64_t tile_stride;    // doubles between consecutive row tiles of the buffer
+  int tile0;              // global row tile stored at the start of the buffer
+  int col0;               // first panel column inside the buffer
+};
+struct VcGemmArgs {       // by-value argument block of k_trsm_panel / k_syrk_ws / k_syrk_tiles
+  double* a;              // (local) matrix, row tiles 0 .. nt-1 (global numbering)
+  int64_t lda;
+  double* b;              // border rows, row tiles nt .. nt+nbt-1
+  int64_t ldb;
+  int nt;
+  int blk, pr, pc;        // block-cyclic distribution: tiles per block (0 = not distributed), grid
+  const double* linv;     // TRSM: 128x128 inverse factor (ld 128)
+  int k0;                 // first panel column in LOCAL elements (operands taken from the matrix)
+  int K;                  // panel depth (multiple of 16)
+  int jt;                 // TRSM: panel tile column (global)
+  int n_main;             // TRSM without tile list: main row tiles handled
+  const int* tiles;       // packed (I | J << 16), global tile indices
+  int ntiles;
+  VcOpSrc src_a, src_b;   // operand sources of the update kernels
+};
 struct VcUpdateCall {     // one trailing / inner update of the factorisation plan
   int k0, K;             // panel columns [k0, k0 + K)
   int64_t tile_off;      // into the device tile list
@@ -104,6 +133,15 @@ enum { VC_SWEEP_FACTOR = 0,   // potrf + TRSM + updates on every row tile (main 
 void vc_chol_init();
 void vc_chol_factor(const VcMatrix& M, VcCholWork& w, int64_t* launches, int mode = VC_SWEEP_FACTOR);
 void vc_chol_free_plans(VcCholWork& w);
+// raw launchers (used by the distributed driver, vc_dist.cu)
+void vc_launch_potrf(double* diag, int64_t lda, int jt, double* linv_all, double* logdet_part, int* info,
+                     bool legacy, cudaStream_t st, int64_t* launches);
+void vc_launch_trsm(const VcGemmArgs& g, int grid, cudaStream_t st, int64_t* launches);
+void vc_launch_syrk(const VcGemmArgs& g, int num_sms, bool legacy, cudaStream_t st, int64_t* launches);
+void vc_launch_reset_info(int* info, cudaStream_t st, int64_t* launches);
+void vc_launch_pack_tiles(const VcGemmArgs& g, const int* tiles, int ntiles, int lcol0, int K, double* dst,
+                          int tile0, cudaStream_t st, int64_t* launches);
+void vc_append_trapezoid(std::vector<int>& out, int J0, int J1, int nrows);
 
 // vc_finalize.cu
 struct VcFinalWork {
@@ -115,6 +153,16 @@ void vc_launch_finalize(const VcMatrix& M, int p, int mu_mode, const double* mu_
                         const double* logdet_part, const int* info, VcFinalWork& fw,
                         double* result_dev, cudaStream_t st, int64_t* launches,
                         double* gram_out_dev = nullptr);
+void vc_launch_gram_local(const double* b, int64_t ldb, int64_t ncols, int p, VcFinalWork& fw, double* gram_dd,
+                          cudaStream_t st, int64_t* launches);
+void vc_launch_sum(const double* v, int n, double* out, cudaStream_t st, int64_t* launches);
+void vc_launch_solve_reduced(const double* gram_dd, int p, int mu_mode, const double* mu_in_dev,
+                             const double* logdet_sum, const int* info, double* result_dev, double* gram_out,
+                             cudaStream_t st, int64_t* launches);
+void vc_launch_quad_local(const double* b, int64_t ldb, int64_t ncols, int p, const double* result_dev,
+                          VcFinalWork& fw, double* quad_dd, cudaStream_t st, int64_t* launches);
+void vc_launch_assemble_reduced(const double* quad_dd, int64_t n, double* result_dev, cudaStream_t st,
+                                int64_t* launches);
 void vc_launch_gather_whitened(const VcMatrix& M, int p, double* z_out_dev, cudaStream_t st,
                                int64_t* launches);
 void vc_launch_extract_chol(const VcMatrix& M, double* r_out_dev, cudaStream_t st,

@@ -1,7 +1,30 @@
-// vc_dist.cu -- K4 (multi-GPU 2D block-cyclic build + Cholesky with NCCL panel broadcasts).
-// Placeholder while the single-GPU path is brought up; the host-only block-cyclic maps are final.
+// vc_dist.cu -- K4: one -2logL evaluation sharded over a pr x pc grid of GPUs (one process per GPU).
+//
+// Sigma_y is built and factored 2D block-cyclic (distribution block = the outer Cholesky block,
+// nb tiles of 128): tile (I, J) lives on process ((I/nb) % pr, (J/nb) % pc) at local tile
+// ((I/nb)/pr * nb + I%nb, (J/nb)/pc * nb + J%nb).  The reference has nothing like it (single R
+// process; optimParallel PSOCK workers, R-pkg/R/SVC_mle.R:164-200): this exists because the fp64
+// Sigma_y of n = 150 000 (180 GB) does not fit one GPU.
+//
+// Per outer block [ob, oe):
+//   1. the owner of the diagonal block factors it locally (k_potrf128b / k_trsm_panel / k_syrk_ws
+//      on its own tiles) and broadcasts L_DD and the nb diagonal-tile inverses (NCCL, 2.5 MB);
+//   2. the ranks of the panel's process column solve their rows against L_DD (TRSM + inner update
+//      per 128-wide sub-panel, operands from the broadcast buffer);
+//   3. they pack their part of the panel tile-major and every distribution block of it is
+//      broadcast by its owner to all ranks (grouped ncclBroadcast over NVLink/NVSwitch);
+//   4. every rank applies the trailing update to the tiles it owns, reading both operands from
+//      the gathered panel buffer.
+// The build is communication-free (each rank evaluates exactly its tiles from replicated O(n)
+// inputs); the finalize needs three tiny all-reduces (Gram, log-det + info, quadratic form).
 #include "vc_handle.cuh"
+#include <dlfcn.h>
+#include <limits.h>
+#include <math.h>
+#include <string.h>
+#include <algorithm>
 
+// ---- host-only block-cyclic maps (exported; unit-tested on the CPU) --------------------------
 extern "C" int vc_bc_owner(int32_t bi, int32_t bj, int32_t pr, int32_t pc) {
   if (pr < 1 || pc < 1 || bi < 0 || bj < 0) return -1;
   return (bi % pr) * pc + (bj % pc);          // row-major process grid
@@ -15,14 +38,417 @@ extern "C" int vc_bc_count(int32_t nblocks, int32_t coord, int32_t nprocs_dim) {
   return (nblocks - coord + nprocs_dim - 1) / nprocs_dim;
 }
 
-extern "C" int vc_nccl_unique_id(char id_out[128]) { (void)id_out; return VC_ERR_INVALID; }
-extern "C" int vc_create_dist(vc_handle** h, const vc_config*, int64_t, int32_t, int32_t, int32_t,
-                              const double*, const double*, const double*, const double*, int32_t,
-                              int32_t, int32_t, int32_t, const char*) {
-  if (h) *h = nullptr;
-  return vc_fail(nullptr, VC_ERR_INVALID, "vc_create_dist: not built yet");
+// trailing-update tiles (packed I | J << 16) that `rank` owns after outer block [.., oe):
+// J in [oe, nt), I in [J, nt + nbt); border tiles (I >= nt) belong to process row 0.
+static void trailing_tiles(int nt, int nbt, int nb, int pr, int pc, int rank, int oe, std::vector<int>& out) {
+  std::vector<int> all;
+  vc_append_trapezoid(all, oe, nt, nt + nbt);
+  const int my_pr = rank / pc, my_pc = rank % pc;
+  for (int t : all) {
+    const int I = t & 0xffff, J = t >> 16;
+    const int orow = (I < nt) ? (I / nb) % pr : 0;
+    if (orow == my_pr && (J / nb) % pc == my_pc) out.push_back(t);
+  }
 }
-int vc_dist_n2ll(vc_handle* h, const double*, int32_t, const double*, double*, double*, double*, double*) {
-  return vc_fail(h, VC_ERR_INVALID, "distributed path not built yet");
+extern "C" int vc_bc_trailing_tiles(int32_t nt, int32_t nbt, int32_t nb, int32_t pr, int32_t pc, int32_t rank,
+                                    int32_t oe, int32_t* out, int32_t cap) {
+  if (nt < 1 || nbt < 0 || nb < 1 || pr < 1 || pc < 1 || rank < 0 || rank >= pr * pc) return -1;
+  std::vector<int> v;
+  trailing_tiles(nt, nbt, nb, pr, pc, rank, oe, v);
+  if (out) for (int i = 0; i < (int)v.size() && i < cap; ++i) out[i] = v[i];
+  return (int)v.size();
 }
-void vc_dist_destroy(vc_handle*) {}
+
+// ---- NCCL through dlopen (the library already loaded by the host process is reused) ----------
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+enum { ncclInt32_ = 2, ncclFloat64_ = 8 };
+enum { ncclSum_ = 0, ncclMin_ = 3 };
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  int (*CommDestroy)(ncclComm_t) = nullptr;
+  int (*Broadcast)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  std::string err;
+  bool load() {
+    if (lib) return true;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* nm : names) {
+      lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+      if (lib) break;
+    }
+    if (!lib) { err = std::string("cannot load libnccl: ") + dlerror(); return false; }
+#define VC_SYM(field, name)                                                   \
+    *(void**)(&field) = dlsym(lib, name);                                     \
+    if (!field) { err = std::string("libnccl lacks ") + name; return false; }
+    VC_SYM(GetUniqueId, "ncclGetUniqueId")
+    VC_SYM(CommInitRank, "ncclCommInitRank")
+    VC_SYM(CommDestroy, "ncclCommDestroy")
+    VC_SYM(Broadcast, "ncclBroadcast")
+    VC_SYM(AllReduce, "ncclAllReduce")
+    VC_SYM(GroupStart, "ncclGroupStart")
+    VC_SYM(GroupEnd, "ncclGroupEnd")
+    VC_SYM(GetErrorString, "ncclGetErrorString")
+#undef VC_SYM
+    return true;
+  }
+};
+static NcclApi g_nccl;
+
+#define VC_NCCL_TRY(expr)                                                                       \
+  do {                                                                                          \
+    int _r = (expr);                                                                            \
+    if (_r != 0) {                                                                              \
+      char _b[512];                                                                             \
+      snprintf(_b, sizeof(_b), "%s failed: %s (%s:%d)", #expr, g_nccl.GetErrorString(_r), __FILE__, __LINE__); \
+      throw VcError(VC_ERR_CUDA, _b);                                                           \
+    }                                                                                           \
+  } while (0)
+
+extern "C" int vc_nccl_unique_id(char id_out[128]) {
+  if (!id_out) return VC_ERR_INVALID;
+  if (!g_nccl.load()) return vc_fail(nullptr, VC_ERR_CUDA, g_nccl.err);
+  ncclUniqueId id;
+  int r = g_nccl.GetUniqueId(&id);
+  if (r != 0) return vc_fail(nullptr, VC_ERR_CUDA, std::string("ncclGetUniqueId: ") + g_nccl.GetErrorString(r));
+  memcpy(id_out, id.internal, 128);
+  return VC_OK;
+}
+
+// ---- the distributed state ---------------------------------------------------------------------
+struct Span { int64_t off; int n; };
+struct BcastOp { int64_t off; int64_t count; int root; };
+struct DistStep {
+  int ob, oe, diag_owner, pcp;
+  // diagonal owner only
+  std::vector<Span> d_trsm, d_inner;     // per sub-panel
+  Span d_pack;
+  // panel-column ranks
+  Span rows;                             // local row tiles >= oe (+ border), packed I
+  std::vector<Span> inner;               // per sub-panel: (I in rows) x (J in (jt, oe))
+  std::vector<BcastOp> bcasts;           // panel blocks, in doubles relative to pnl
+  Span trailing;
+};
+struct VcDist {
+  int rank = 0, world = 1, pr = 1, pc = 1, my_pr = 0, my_pc = 0;
+  ncclComm_t comm = nullptr;
+  int nt = 0, nbt = 1, nb = 4;
+  int lrt = 0, lct = 0;
+  int64_t lda = 0;
+  std::vector<int> col_tiles;
+  int* col_tiles_dev = nullptr;
+  int* tiles_dev = nullptr;
+  Span build;
+  std::vector<DistStep> steps;
+  double* dd = nullptr;       // nb tiles x (128 x nb*128) + nb x (128 x 128) inverses
+  double* pnl = nullptr;
+  double* red = nullptr;      // [gram pairs*2 | logdet | quad(2)]
+  int* info_red = nullptr;
+};
+
+static inline int loc_tile_h(int t, int nb, int P) { return ((t / nb) / P) * nb + t % nb; }
+
+void vc_dist_destroy(vc_handle* h) {
+  VcDist* D = (VcDist*)h->dist;
+  if (!D) return;
+  if (D->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(D->comm);
+  cudaFree(D->col_tiles_dev); cudaFree(D->tiles_dev); cudaFree(D->dd); cudaFree(D->pnl);
+  cudaFree(D->red); cudaFree(D->info_red);
+  delete D;
+  h->dist = nullptr;
+}
+
+static void build_dist_plan(vc_handle* h, VcDist* D) {
+  const int nt = D->nt, nbt = D->nbt, nb = D->nb, pr = D->pr, pc = D->pc;
+  const int nblocks = (nt + nb - 1) / nb;
+  std::vector<int> tiles;
+  auto span_begin = [&]() { return (int64_t)tiles.size(); };
+  auto span_end = [&](int64_t off) { Span s; s.off = off; s.n = (int)((int64_t)tiles.size() - off); return s; };
+  auto own_row = [&](int I) { return (I < nt ? (I / nb) % pr : 0) == D->my_pr; };
+  auto own_col = [&](int J) { return (J / nb) % pc == D->my_pc; };
+  // build list: local lower tiles (diagonal tiles in full)
+  {
+    const int64_t off = span_begin();
+    for (int J = 0; J < nt; ++J)
+      if (own_col(J))
+        for (int I = J; I < nt; ++I)
+          if (own_row(I)) tiles.push_back(I | (J << 16));
+    D->build = span_end(off);
+  }
+  for (int b = 0; b < nblocks; ++b) {
+    DistStep st;
+    st.ob = b * nb;
+    st.oe = std::min(st.ob + nb, nt);
+    st.pcp = b % pc;
+    st.diag_owner = (b % pr) * pc + st.pcp;
+    const int Kb = (st.oe - st.ob) * VC_TILE;
+    if (D->rank == st.diag_owner) {
+      for (int jt = st.ob; jt < st.oe; ++jt) {
+        int64_t off = span_begin();
+        for (int I = jt + 1; I < st.oe; ++I) tiles.push_back(I | (jt << 16));
+        st.d_trsm.push_back(span_end(off));
+        off = span_begin();
+        for (int J = jt + 1; J < st.oe; ++J)
+          for (int I = J; I < st.oe; ++I) tiles.push_back(I | (J << 16));
+        st.d_inner.push_back(span_end(off));
+      }
+      const int64_t off = span_begin();
+      for (int I = st.ob; I < st.oe; ++I) tiles.push_back(I);
+      st.d_pack = span_end(off);
+    }
+    if (D->my_pc == st.pcp) {
+      int64_t off = span_begin();
+      for (int I = st.oe; I < nt + nbt; ++I)
+        if (own_row(I)) tiles.push_back(I | (st.ob << 16));
+      st.rows = span_end(off);
+      std::vector<int> rows(tiles.begin() + st.rows.off, tiles.end());
+      for (int jt = st.ob; jt < st.oe; ++jt) {
+        off = span_begin();
+        for (int J = jt + 1; J < st.oe; ++J)
+          for (int I : rows) tiles.push_back((I & 0xffff) | (J << 16));
+        st.inner.push_back(span_end(off));
+      }
+    }
+    // panel broadcasts: every distribution block of rows >= oe, then the border
+    for (int B = st.oe / nb + (st.oe % nb ? 1 : 0); B < nblocks; ++B) {
+      const int t0 = B * nb, t1 = std::min(t0 + nb, nt);
+      BcastOp op;
+      op.off = (int64_t)(t0 - st.oe) * VC_TILE * Kb;
+      op.count = (int64_t)(t1 - t0) * VC_TILE * Kb;
+      op.root = (B % pr) * pc + st.pcp;
+      st.bcasts.push_back(op);
+    }
+    if (st.oe < nt) {
+      BcastOp op;
+      op.off = (int64_t)(nt - st.oe) * VC_TILE * Kb;
+      op.count = (int64_t)nbt * VC_TILE * Kb;
+      op.root = 0 * pc + st.pcp;
+      st.bcasts.push_back(op);
+    }
+    {
+      const int64_t off = span_begin();
+      if (st.oe < nt) trailing_tiles(nt, nbt, nb, pr, pc, D->rank, st.oe, tiles);
+      st.trailing = span_end(off);
+    }
+    D->steps.push_back(st);
+  }
+  VC_CUDA_TRY(cudaMalloc(&D->tiles_dev, std::max<size_t>(tiles.size(), 1) * sizeof(int)));
+  if (!tiles.empty())
+    VC_CUDA_TRY(cudaMemcpy(D->tiles_dev, tiles.data(), tiles.size() * sizeof(int), cudaMemcpyHostToDevice));
+  (void)h;
+}
+
+extern "C" int vc_create_dist(vc_handle** out, const vc_config* cfg_in, int64_t n, int32_t d, int32_t p,
+                              int32_t q, const double* locs, const double* X, const double* W,
+                              const double* y, int32_t rank, int32_t world, int32_t pr, int32_t pc,
+                              const char nccl_id[128]) {
+  if (!out) return VC_ERR_INVALID;
+  *out = nullptr;
+  vc_config cfg;
+  if (cfg_in) cfg = *cfg_in; else vc_config_default(&cfg);
+  if (!locs || !X || !W || !y || !nccl_id) return vc_fail(nullptr, VC_ERR_INVALID, "NULL input pointer");
+  if (pr < 1 || pc < 1 || pr * pc != world || rank < 0 || rank >= world)
+    return vc_fail(nullptr, VC_ERR_INVALID, "process grid pr x pc must equal the world size");
+  std::string why;
+  if (vc_validate_cfg(&cfg, n, d, p, q, why) != VC_OK) return vc_fail(nullptr, VC_ERR_INVALID, why);
+  if (!g_nccl.load()) return vc_fail(nullptr, VC_ERR_CUDA, g_nccl.err);
+  vc_handle* h = nullptr;
+  VcDist* D = nullptr;
+  try {
+    h = vc_alloc_common(&cfg, n, d, p, q, locs, X, W, y, /*alloc_matrix=*/false);
+    D = new VcDist();
+    h->dist = D;
+    D->rank = rank; D->world = world; D->pr = pr; D->pc = pc;
+    D->my_pr = rank / pc; D->my_pc = rank % pc;
+    D->nt = h->M.nt; D->nbt = 1; D->nb = h->cw.nb_tiles;
+    const int nb = D->nb, nt = D->nt;
+    const int nblocks = (nt + nb - 1) / nb;
+    // local shapes
+    int lrt = 0, lct = 0;
+    for (int b = 0; b < nblocks; ++b) {
+      const int tiles_in = std::min(nb, nt - b * nb);
+      if (b % pr == D->my_pr) lrt += tiles_in;
+      if (b % pc == D->my_pc) {
+        for (int t = 0; t < tiles_in; ++t) D->col_tiles.push_back(b * nb + t);
+        lct += tiles_in;
+      }
+    }
+    D->lrt = lrt; D->lct = lct;
+    D->lda = (int64_t)std::max(lrt, 1) * VC_TILE + VC_TILE;
+    h->M.lda = D->lda;
+    h->M.ldb = VC_BORDER_ROWS;
+    h->M.nbt = 1;
+    VC_CUDA_TRY(cudaMalloc(&h->M.a, (size_t)D->lda * std::max(lct, 1) * VC_TILE * sizeof(double)));
+    VC_CUDA_TRY(cudaMalloc(&h->M.b, (size_t)h->M.ldb * std::max(lct, 1) * VC_TILE * sizeof(double)));
+    VC_CUDA_TRY(cudaMalloc(&h->cw.logdet_part, (size_t)nt * sizeof(double)));
+    VC_CUDA_TRY(cudaMalloc(&D->col_tiles_dev, std::max<size_t>(D->col_tiles.size(), 1) * sizeof(int)));
+    if (!D->col_tiles.empty())
+      VC_CUDA_TRY(cudaMemcpy(D->col_tiles_dev, D->col_tiles.data(), D->col_tiles.size() * sizeof(int),
+                             cudaMemcpyHostToDevice));
+    const int64_t Kmax = (int64_t)nb * VC_TILE;
+    VC_CUDA_TRY(cudaMalloc(&D->dd, ((size_t)nb * VC_TILE * Kmax + (size_t)nb * VC_TILE * VC_TILE) * sizeof(double)));
+    VC_CUDA_TRY(cudaMalloc(&D->pnl, (size_t)(nt + 1) * VC_TILE * Kmax * sizeof(double)));
+    const int m = p + 1;
+    VC_CUDA_TRY(cudaMalloc(&D->red, ((size_t)m * (m + 1) + 8) * sizeof(double)));
+    VC_CUDA_TRY(cudaMalloc(&D->info_red, sizeof(int)));
+    build_dist_plan(h, D);
+    ncclUniqueId id;
+    memcpy(id.internal, nccl_id, 128);
+    VC_NCCL_TRY(g_nccl.CommInitRank(&D->comm, world, id, rank));
+  } catch (const VcError& e) {
+    if (h) vc_free_handle(h);
+    return vc_fail(nullptr, e.code, e.msg);
+  }
+  *out = h;
+  return VC_OK;
+}
+
+int vc_dist_n2ll(vc_handle* h, const double* theta, int32_t mu_mode, const double* mu_in,
+                 double* n2ll, double* mu_out, double* logdet, double* quad) {
+  VcDist* D = (VcDist*)h->dist;
+  if (!D) return VC_ERR_INVALID;
+  if (mu_mode != VC_MU_GLS && mu_mode != VC_MU_FIXED) return vc_fail(h, VC_ERR_INVALID, "unknown mu_mode");
+  if (mu_mode == VC_MU_FIXED && !mu_in) return vc_fail(h, VC_ERR_INVALID, "mu_mode FIXED needs mu");
+  VcTheta th;
+  if (vc_make_theta(h, theta, &th) != VC_OK)
+    return vc_fail(h, VC_ERR_INVALID, "theta does not define a covariance (range <= 0 or non-finite value)");
+  try {
+    VC_CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t st = h->st_main;
+    const int nt = D->nt, nb = D->nb, p = h->p;
+    const int m = p + 1, npairs = m * (m + 1) / 2;
+    if (mu_mode == VC_MU_FIXED)
+      VC_CUDA_TRY(cudaMemcpyAsync(h->mu_in, mu_in, p * sizeof(double), cudaMemcpyHostToDevice, st));
+    VC_CUDA_TRY(cudaEventRecord(h->ev[0], st));
+    VC_CUDA_TRY(cudaMemsetAsync(h->cw.logdet_part, 0, (size_t)nt * sizeof(double), st));
+    vc_launch_reset_info(h->cw.info, st, &h->launches);
+    vc_launch_build_tiles(h->M.a, h->M.lda, h->n, h->n_pad, th, h->d, h->locs, h->w,
+                          D->tiles_dev + D->build.off, D->build.n, nb, D->pr, D->pc, st, &h->launches);
+    if (D->my_pr == 0)
+      vc_launch_border_dist(h->M.b, h->M.ldb, h->n_pad, p, h->x, h->y, D->col_tiles_dev, D->lct, st, &h->launches);
+    VC_CUDA_TRY(cudaEventRecord(h->ev[1], st));
+
+    VcGemmArgs base{};
+    base.a = h->M.a; base.lda = h->M.lda; base.b = h->M.b; base.ldb = h->M.ldb; base.nt = nt;
+    base.blk = nb; base.pr = D->pr; base.pc = D->pc;
+    for (const DistStep& s : D->steps) {
+      const int nsub = s.oe - s.ob;
+      const int Kb = nsub * VC_TILE;
+      double* dd_linv = D->dd + (size_t)nb * VC_TILE * ((size_t)nb * VC_TILE);
+      if (D->rank == s.diag_owner) {
+        for (int jt = s.ob; jt < s.oe; ++jt) {
+          const int i = jt - s.ob;
+          double* diag = h->M.a + (int64_t)loc_tile_h(jt, nb, D->pr) * VC_TILE +
+                         (int64_t)loc_tile_h(jt, nb, D->pc) * VC_TILE * h->M.lda;
+          // potrf indexes its inverse slot by jt: bias the base so that slot jt is dd_linv[jt - ob]
+          vc_launch_potrf(diag, h->M.lda, jt, dd_linv - (int64_t)s.ob * VC_TILE * VC_TILE, h->cw.logdet_part,
+                          h->cw.info, h->cw.legacy_potrf, st, &h->launches);
+          VcGemmArgs g = base;
+          g.linv = dd_linv + (size_t)i * VC_TILE * VC_TILE;
+          g.jt = jt; g.K = VC_TILE;
+          g.k0 = loc_tile_h(jt, nb, D->pc) * VC_TILE;
+          g.tiles = D->tiles_dev + s.d_trsm[i].off; g.ntiles = s.d_trsm[i].n;
+          vc_launch_trsm(g, g.ntiles, st, &h->launches);
+          g.tiles = D->tiles_dev + s.d_inner[i].off; g.ntiles = s.d_inner[i].n;
+          vc_launch_syrk(g, h->cw.num_sms, h->cw.legacy_syrk, st, &h->launches);
+        }
+        vc_launch_pack_tiles(base, D->tiles_dev + s.d_pack.off, s.d_pack.n,
+                             loc_tile_h(s.ob, nb, D->pc) * VC_TILE, Kb, D->dd, s.ob, st, &h->launches);
+      }
+      if (D->world > 1)
+        VC_NCCL_TRY(g_nccl.Broadcast(D->dd, D->dd, (size_t)nb * VC_TILE * ((size_t)nb * VC_TILE) +
+                                                       (size_t)nb * VC_TILE * VC_TILE,
+                                     ncclFloat64_, s.diag_owner, D->comm, st));
+      if (D->my_pc == s.pcp && s.rows.n > 0) {
+        for (int jt = s.ob; jt < s.oe; ++jt) {
+          const int i = jt - s.ob;
+          VcGemmArgs g = base;
+          g.linv = dd_linv + (size_t)i * VC_TILE * VC_TILE;
+          g.jt = jt; g.K = VC_TILE;
+          g.k0 = loc_tile_h(jt, nb, D->pc) * VC_TILE;
+          g.tiles = D->tiles_dev + s.rows.off; g.ntiles = s.rows.n;
+          vc_launch_trsm(g, g.ntiles, st, &h->launches);
+          g.tiles = D->tiles_dev + s.inner[i].off; g.ntiles = s.inner[i].n;
+          g.src_b.pnl = D->dd; g.src_b.ld = VC_TILE; g.src_b.tile_stride = (int64_t)VC_TILE * Kb;
+          g.src_b.tile0 = s.ob; g.src_b.col0 = i * VC_TILE;
+          vc_launch_syrk(g, h->cw.num_sms, h->cw.legacy_syrk, st, &h->launches);
+        }
+        vc_launch_pack_tiles(base, D->tiles_dev + s.rows.off, s.rows.n,
+                             loc_tile_h(s.ob, nb, D->pc) * VC_TILE, Kb, D->pnl, s.oe, st, &h->launches);
+      }
+      if (s.oe >= nt) continue;
+      if (D->world > 1) {
+        VC_NCCL_TRY(g_nccl.GroupStart());
+        for (const BcastOp& op : s.bcasts)
+          VC_NCCL_TRY(g_nccl.Broadcast(D->pnl + op.off, D->pnl + op.off, (size_t)op.count, ncclFloat64_, op.root,
+                                       D->comm, st));
+        VC_NCCL_TRY(g_nccl.GroupEnd());
+      }
+      VcGemmArgs g = base;
+      g.K = Kb;
+      g.tiles = D->tiles_dev + s.trailing.off; g.ntiles = s.trailing.n;
+      g.src_a.pnl = D->pnl; g.src_a.ld = VC_TILE; g.src_a.tile_stride = (int64_t)VC_TILE * Kb;
+      g.src_a.tile0 = s.oe; g.src_a.col0 = 0;
+      g.src_b = g.src_a;
+      vc_launch_syrk(g, h->cw.num_sms, h->cw.legacy_syrk, st, &h->launches);
+    }
+    VC_CUDA_TRY(cudaEventRecord(h->ev[2], st));
+
+    // ---- finalize: local partials, three small all-reduces ----
+    double* red_gram = D->red;
+    double* red_logdet = D->red + 2 * npairs;
+    double* red_quad = red_logdet + 2;
+    if (D->my_pr == 0 && D->lct > 0)
+      vc_launch_gram_local(h->M.b, h->M.ldb, (int64_t)D->lct * VC_TILE, p, h->fw, red_gram, st, &h->launches);
+    else
+      VC_CUDA_TRY(cudaMemsetAsync(red_gram, 0, 2 * npairs * sizeof(double), st));
+    vc_launch_sum(h->cw.logdet_part, nt, red_logdet, st, &h->launches);
+    if (D->world > 1) {
+      VC_NCCL_TRY(g_nccl.AllReduce(D->red, D->red, 2 * npairs + 1, ncclFloat64_, ncclSum_, D->comm, st));
+      VC_NCCL_TRY(g_nccl.AllReduce(h->cw.info, D->info_red, 1, ncclInt32_, ncclMin_, D->comm, st));
+    } else {
+      VC_CUDA_TRY(cudaMemcpyAsync(D->info_red, h->cw.info, sizeof(int), cudaMemcpyDeviceToDevice, st));
+    }
+    vc_launch_solve_reduced(red_gram, p, mu_mode, h->mu_in, red_logdet, D->info_red, h->results, h->gram_dev,
+                            st, &h->launches);
+    if (D->my_pr == 0 && D->lct > 0)
+      vc_launch_quad_local(h->M.b, h->M.ldb, (int64_t)D->lct * VC_TILE, p, h->results, h->fw, red_quad, st,
+                           &h->launches);
+    else
+      VC_CUDA_TRY(cudaMemsetAsync(red_quad, 0, 2 * sizeof(double), st));
+    if (D->world > 1)
+      VC_NCCL_TRY(g_nccl.AllReduce(red_quad, red_quad, 2, ncclFloat64_, ncclSum_, D->comm, st));
+    vc_launch_assemble_reduced(red_quad, h->n, h->results, st, &h->launches);
+    VC_CUDA_TRY(cudaEventRecord(h->ev[3], st));
+    VC_CUDA_TRY(cudaMemcpyAsync(h->results_host, h->results, VC_RES_STRIDE * sizeof(double),
+                                cudaMemcpyDeviceToHost, st));
+    VC_CUDA_TRY(cudaStreamSynchronize(st));
+    VC_CUDA_TRY(cudaGetLastError());
+    const double* r = h->results_host;
+    float b = 0, c = 0, f = 0;
+    cudaEventElapsedTime(&b, h->ev[0], h->ev[1]);
+    cudaEventElapsedTime(&c, h->ev[1], h->ev[2]);
+    cudaEventElapsedTime(&f, h->ev[2], h->ev[3]);
+    h->last_timing = {b, c, f, b + c + f};
+    *n2ll = r[VC_RES_N2LL];
+    if (mu_out) for (int i = 0; i < p; ++i) mu_out[i] = r[VC_RES_MU + i];
+    if (logdet) *logdet = r[VC_RES_LOGDET];
+    if (quad) *quad = r[VC_RES_QUAD];
+    const int info = (int)r[VC_RES_INFO];
+    h->last_info = info;
+    if (info != 0) {
+      char buf[128];
+      snprintf(buf, sizeof(buf), "the leading minor of order %d is not positive", info);
+      h->err = buf;
+      return VC_ERR_NOT_PD;
+    }
+  } catch (const VcError& e) {
+    return vc_fail(h, e.code, e.msg);
+  }
+  return VC_OK;
+}

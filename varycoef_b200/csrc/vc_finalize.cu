@@ -217,7 +217,62 @@ __global__ void k_extract_chol(const double* __restrict__ a, int64_t lda, int64_
   }
 }
 
+// out[2i] = sum over blocks of (hi + lo) of pair i, out[2i+1] = 0 (fixed order); distributed finalize
+__global__ void k_reduce_dd(const double* __restrict__ part, int blocks, int count, double* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  double hi = 0.0, lo = 0.0;
+  for (int b = 0; b < blocks; ++b) dd_add(hi, lo, part[(int64_t)b * 2 * count + 2 * i], part[(int64_t)b * 2 * count + 2 * i + 1]);
+  out[2 * i] = hi + lo;
+  out[2 * i + 1] = 0.0;
+}
+__global__ void k_sum_serial(const double* __restrict__ v, int n, double* __restrict__ out) {
+  double s = 0.0, c = 0.0;
+  for (int i = 0; i < n; ++i) {
+    const double yv = v[i] - c;
+    const double t = s + yv;
+    c = (t - s) - yv;
+    s = t;
+  }
+  *out = s;
+}
+
 }  // namespace
+
+// pieces of the finalize for the distributed driver (an NCCL all-reduce goes between them)
+void vc_launch_gram_local(const double* b, int64_t ldb, int64_t ncols, int p, VcFinalWork& fw, double* gram_dd,
+                          cudaStream_t st, int64_t* launches) {
+  const int m = p + 1, npairs = m * (m + 1) / 2;
+  const size_t sm1 = ((size_t)m * CHUNK + 2 * (size_t)npairs) * sizeof(double);
+  cudaFuncSetAttribute(k_gram_partial, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  k_gram_partial<<<fw.blocks, FIN_THREADS, sm1, st>>>(b, ldb, ncols, p, fw.gram_part);
+  k_reduce_dd<<<(npairs + 127) / 128, 128, 0, st>>>(fw.gram_part, fw.blocks, npairs, gram_dd);
+  *launches += 2;
+}
+void vc_launch_sum(const double* v, int n, double* out, cudaStream_t st, int64_t* launches) {
+  k_sum_serial<<<1, 1, 0, st>>>(v, n, out);
+  ++*launches;
+}
+void vc_launch_solve_reduced(const double* gram_dd, int p, int mu_mode, const double* mu_in_dev,
+                             const double* logdet_sum, const int* info, double* result_dev, double* gram_out,
+                             cudaStream_t st, int64_t* launches) {
+  const int m = p + 1;
+  const size_t sm2 = ((size_t)m * m + p + 1) * sizeof(double);
+  cudaFuncSetAttribute(k_solve_mu, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  k_solve_mu<<<1, FIN_THREADS, sm2, st>>>(gram_dd, 1, p, mu_mode, mu_in_dev, logdet_sum, 1, info, result_dev, gram_out);
+  ++*launches;
+}
+void vc_launch_quad_local(const double* b, int64_t ldb, int64_t ncols, int p, const double* result_dev,
+                          VcFinalWork& fw, double* quad_dd, cudaStream_t st, int64_t* launches) {
+  k_quad_partial<<<fw.blocks, FIN_THREADS, 0, st>>>(b, ldb, ncols, p, result_dev, fw.quad_part);
+  k_reduce_dd<<<1, 32, 0, st>>>(fw.quad_part, fw.blocks, 1, quad_dd);
+  *launches += 2;
+}
+void vc_launch_assemble_reduced(const double* quad_dd, int64_t n, double* result_dev, cudaStream_t st,
+                                int64_t* launches) {
+  k_assemble<<<1, 1, 0, st>>>(quad_dd, 1, n, result_dev);
+  ++*launches;
+}
 
 void vc_launch_finalize(const VcMatrix& M, int p, int mu_mode, const double* mu_in_dev,
                         const double* logdet_part, const int* info, VcFinalWork& fw,
