@@ -132,7 +132,7 @@ struct DistStep {
   Span rows;                             // local row tiles >= oe (+ border), packed I
   std::vector<Span> inner;               // per sub-panel: (I in rows) x (J in (jt, oe))
   std::vector<BcastOp> bcasts;           // panel blocks, in doubles relative to pnl
-  Span trailing;
+  Span trailing_col, trailing_rest;      // next block's columns first (lookahead), then the rest
 };
 struct VcDist {
   int rank = 0, world = 1, pr = 1, pc = 1, my_pr = 0, my_pc = 0;
@@ -146,7 +146,7 @@ struct VcDist {
   Span build;
   std::vector<DistStep> steps;
   double* dd = nullptr;       // nb tiles x (128 x nb*128) + nb x (128 x 128) inverses
-  double* pnl = nullptr;
+  double* pnl[2] = {nullptr, nullptr};   // double-buffered gathered panel (lookahead)
   double* red = nullptr;      // [gram pairs*2 | logdet | quad(2)]
   int* info_red = nullptr;
 };
@@ -157,7 +157,7 @@ void vc_dist_destroy(vc_handle* h) {
   VcDist* D = (VcDist*)h->dist;
   if (!D) return;
   if (D->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(D->comm);
-  cudaFree(D->col_tiles_dev); cudaFree(D->tiles_dev); cudaFree(D->dd); cudaFree(D->pnl);
+  cudaFree(D->col_tiles_dev); cudaFree(D->tiles_dev); cudaFree(D->dd); cudaFree(D->pnl[0]); cudaFree(D->pnl[1]);
   cudaFree(D->red); cudaFree(D->info_red);
   delete D;
   h->dist = nullptr;
@@ -231,9 +231,15 @@ static void build_dist_plan(vc_handle* h, VcDist* D) {
       st.bcasts.push_back(op);
     }
     {
-      const int64_t off = span_begin();
-      if (st.oe < nt) trailing_tiles(nt, nbt, nb, pr, pc, D->rank, st.oe, tiles);
-      st.trailing = span_end(off);
+      std::vector<int> tr;
+      if (st.oe < nt) trailing_tiles(nt, nbt, nb, pr, pc, D->rank, st.oe, tr);
+      const int ne = std::min(st.oe + nb, nt);
+      int64_t off = span_begin();
+      for (int t : tr) if ((t >> 16) < ne) tiles.push_back(t);
+      st.trailing_col = span_end(off);
+      off = span_begin();
+      for (int t : tr) if ((t >> 16) >= ne) tiles.push_back(t);
+      st.trailing_rest = span_end(off);
     }
     D->steps.push_back(st);
   }
@@ -292,7 +298,8 @@ extern "C" int vc_create_dist(vc_handle** out, const vc_config* cfg_in, int64_t 
                              cudaMemcpyHostToDevice));
     const int64_t Kmax = (int64_t)nb * VC_TILE;
     VC_CUDA_TRY(cudaMalloc(&D->dd, ((size_t)nb * VC_TILE * Kmax + (size_t)nb * VC_TILE * VC_TILE) * sizeof(double)));
-    VC_CUDA_TRY(cudaMalloc(&D->pnl, (size_t)(nt + 1) * VC_TILE * Kmax * sizeof(double)));
+    for (int i = 0; i < 2; ++i)
+      VC_CUDA_TRY(cudaMalloc(&D->pnl[i], (size_t)(nt + 1) * VC_TILE * Kmax * sizeof(double)));
     const int m = p + 1;
     VC_CUDA_TRY(cudaMalloc(&D->red, ((size_t)m * (m + 1) + 8) * sizeof(double)));
     VC_CUDA_TRY(cudaMalloc(&D->info_red, sizeof(int)));
@@ -336,10 +343,25 @@ int vc_dist_n2ll(vc_handle* h, const double* theta, int32_t mu_mode, const doubl
     VcGemmArgs base{};
     base.a = h->M.a; base.lda = h->M.lda; base.b = h->M.b; base.ldb = h->M.ldb; base.nt = nt;
     base.blk = nb; base.pr = D->pr; base.pc = D->pc;
+    // Lookahead: the panel phase of block s+1 (factor / broadcasts / solves, stream sp) overlaps the
+    // "rest" part of the trailing update of block s (stream sm).  All NCCL calls are on sp, in the
+    // same order on every rank.  A persistent update kernel never yields an SM, so the rest update
+    // leaves a few SMs to the panel stream and to NCCL's own kernels.
+    const bool la = h->cw.lookahead;
+    cudaStream_t sm = st, sp = la ? h->st_panel : st;
+    const int reserve = (la && !h->cw.legacy_syrk) ? 8 : 0;
+    if (la) {
+      VC_CUDA_TRY(cudaEventRecord(h->cw.ev_update, sm));
+      VC_CUDA_TRY(cudaStreamWaitEvent(sp, h->cw.ev_update, 0));
+    }
+    int sidx = 0;
     for (const DistStep& s : D->steps) {
       const int nsub = s.oe - s.ob;
       const int Kb = nsub * VC_TILE;
+      double* pnl = D->pnl[sidx & 1];
+      ++sidx;
       double* dd_linv = D->dd + (size_t)nb * VC_TILE * ((size_t)nb * VC_TILE);
+      // ---------------- panel phase (stream sp) ----------------
       if (D->rank == s.diag_owner) {
         for (int jt = s.ob; jt < s.oe; ++jt) {
           const int i = jt - s.ob;
@@ -347,23 +369,23 @@ int vc_dist_n2ll(vc_handle* h, const double* theta, int32_t mu_mode, const doubl
                          (int64_t)loc_tile_h(jt, nb, D->pc) * VC_TILE * h->M.lda;
           // potrf indexes its inverse slot by jt: bias the base so that slot jt is dd_linv[jt - ob]
           vc_launch_potrf(diag, h->M.lda, jt, dd_linv - (int64_t)s.ob * VC_TILE * VC_TILE, h->cw.logdet_part,
-                          h->cw.info, h->cw.legacy_potrf, st, &h->launches);
+                          h->cw.info, h->cw.legacy_potrf, sp, &h->launches);
           VcGemmArgs g = base;
           g.linv = dd_linv + (size_t)i * VC_TILE * VC_TILE;
           g.jt = jt; g.K = VC_TILE;
           g.k0 = loc_tile_h(jt, nb, D->pc) * VC_TILE;
           g.tiles = D->tiles_dev + s.d_trsm[i].off; g.ntiles = s.d_trsm[i].n;
-          vc_launch_trsm(g, g.ntiles, st, &h->launches);
+          vc_launch_trsm(g, g.ntiles, sp, &h->launches);
           g.tiles = D->tiles_dev + s.d_inner[i].off; g.ntiles = s.d_inner[i].n;
-          vc_launch_syrk(g, h->cw.num_sms, h->cw.legacy_syrk, st, &h->launches);
+          vc_launch_syrk(g, h->cw.num_sms, h->cw.legacy_syrk, sp, &h->launches);
         }
         vc_launch_pack_tiles(base, D->tiles_dev + s.d_pack.off, s.d_pack.n,
-                             loc_tile_h(s.ob, nb, D->pc) * VC_TILE, Kb, D->dd, s.ob, st, &h->launches);
+                             loc_tile_h(s.ob, nb, D->pc) * VC_TILE, Kb, D->dd, s.ob, sp, &h->launches);
       }
       if (D->world > 1)
         VC_NCCL_TRY(g_nccl.Broadcast(D->dd, D->dd, (size_t)nb * VC_TILE * ((size_t)nb * VC_TILE) +
                                                        (size_t)nb * VC_TILE * VC_TILE,
-                                     ncclFloat64_, s.diag_owner, D->comm, st));
+                                     ncclFloat64_, s.diag_owner, D->comm, sp));
       if (D->my_pc == s.pcp && s.rows.n > 0) {
         for (int jt = s.ob; jt < s.oe; ++jt) {
           const int i = jt - s.ob;
@@ -372,30 +394,47 @@ int vc_dist_n2ll(vc_handle* h, const double* theta, int32_t mu_mode, const doubl
           g.jt = jt; g.K = VC_TILE;
           g.k0 = loc_tile_h(jt, nb, D->pc) * VC_TILE;
           g.tiles = D->tiles_dev + s.rows.off; g.ntiles = s.rows.n;
-          vc_launch_trsm(g, g.ntiles, st, &h->launches);
+          vc_launch_trsm(g, g.ntiles, sp, &h->launches);
           g.tiles = D->tiles_dev + s.inner[i].off; g.ntiles = s.inner[i].n;
           g.src_b.pnl = D->dd; g.src_b.ld = VC_TILE; g.src_b.tile_stride = (int64_t)VC_TILE * Kb;
           g.src_b.tile0 = s.ob; g.src_b.col0 = i * VC_TILE;
-          vc_launch_syrk(g, h->cw.num_sms, h->cw.legacy_syrk, st, &h->launches);
+          vc_launch_syrk(g, h->cw.num_sms, h->cw.legacy_syrk, sp, &h->launches);
         }
         vc_launch_pack_tiles(base, D->tiles_dev + s.rows.off, s.rows.n,
-                             loc_tile_h(s.ob, nb, D->pc) * VC_TILE, Kb, D->pnl, s.oe, st, &h->launches);
+                             loc_tile_h(s.ob, nb, D->pc) * VC_TILE, Kb, pnl, s.oe, sp, &h->launches);
       }
       if (s.oe >= nt) continue;
       if (D->world > 1) {
         VC_NCCL_TRY(g_nccl.GroupStart());
         for (const BcastOp& op : s.bcasts)
-          VC_NCCL_TRY(g_nccl.Broadcast(D->pnl + op.off, D->pnl + op.off, (size_t)op.count, ncclFloat64_, op.root,
-                                       D->comm, st));
+          VC_NCCL_TRY(g_nccl.Broadcast(pnl + op.off, pnl + op.off, (size_t)op.count, ncclFloat64_, op.root,
+                                       D->comm, sp));
         VC_NCCL_TRY(g_nccl.GroupEnd());
+      }
+      // ---------------- trailing update (stream sm) ----------------
+      if (la) {
+        VC_CUDA_TRY(cudaEventRecord(h->cw.ev_panel, sp));
+        VC_CUDA_TRY(cudaStreamWaitEvent(sm, h->cw.ev_panel, 0));
       }
       VcGemmArgs g = base;
       g.K = Kb;
-      g.tiles = D->tiles_dev + s.trailing.off; g.ntiles = s.trailing.n;
-      g.src_a.pnl = D->pnl; g.src_a.ld = VC_TILE; g.src_a.tile_stride = (int64_t)VC_TILE * Kb;
+      g.src_a.pnl = pnl; g.src_a.ld = VC_TILE; g.src_a.tile_stride = (int64_t)VC_TILE * Kb;
       g.src_a.tile0 = s.oe; g.src_a.col0 = 0;
       g.src_b = g.src_a;
-      vc_launch_syrk(g, h->cw.num_sms, h->cw.legacy_syrk, st, &h->launches);
+      g.tiles = D->tiles_dev + s.trailing_col.off; g.ntiles = s.trailing_col.n;
+      vc_launch_syrk(g, h->cw.num_sms, h->cw.legacy_syrk, sm, &h->launches);
+      if (la) {
+        // the next panel phase may start once its columns are up to date; it also must not
+        // overwrite the panel buffer the update two steps back was reading (ordered before on sm)
+        VC_CUDA_TRY(cudaEventRecord(h->cw.ev_col, sm));
+        VC_CUDA_TRY(cudaStreamWaitEvent(sp, h->cw.ev_col, 0));
+      }
+      g.tiles = D->tiles_dev + s.trailing_rest.off; g.ntiles = s.trailing_rest.n;
+      vc_launch_syrk(g, h->cw.num_sms - reserve, h->cw.legacy_syrk, sm, &h->launches);
+    }
+    if (la) {
+      VC_CUDA_TRY(cudaEventRecord(h->cw.ev_panel, sp));
+      VC_CUDA_TRY(cudaStreamWaitEvent(sm, h->cw.ev_panel, 0));
     }
     VC_CUDA_TRY(cudaEventRecord(h->ev[2], st));
 
