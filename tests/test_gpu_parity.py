@@ -343,3 +343,98 @@ def test_block_cyclic_driver_on_a_1x1_grid_matches_plain_path(n, p, nb):
         from varycoef_b200 import _lib
         with pytest.raises(_lib.NotPositiveDefinite):
             obj.n2LL(bad)
+
+
+# ---------------------------------------------------------------------------------------------
+# next-tier rows: prep_par_output / eff_dof / predict / GLS_chol on the GPU factor
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,p,cov", [(100, 2, "exp"), (900, 3, "mat32"), (2300, 2, "exp")])
+def test_post_matches_prep_par_output_and_eff_dof(n, p, cov):
+    o = _oracle()
+    from varycoef_b200 import SVCObjective
+    locs, X, W, y = synth(n, p, 31 + n, 2)
+    theta = theta_for(p)
+    D = o.own_dist(locs)
+    S = o.sigma_y(theta, D, W, cov)
+    with SVCObjective(y, X, locs, cov_name=cov, profileLik=True) as obj:
+        post = obj.post(theta)
+        ref = o.prep_par_output(theta, S, X, y, None, p, True)
+        assert np.allclose(post["mu_gls"], ref["FE"]["est"], rtol=1e-9)
+        assert np.allclose(np.sqrt(np.diag(post["Sigma_FE"])), ref["FE"]["SE"], rtol=1e-9)
+        assert np.allclose(post["Sigma_FE"], np.linalg.inv(X.T @ np.linalg.solve(S, X)), rtol=1e-8)
+        assert post["edof"] == pytest.approx(o.eff_dof(theta, X, S), rel=1e-9)
+        # the factor is still resident: the objective at the same theta costs no new factorisation
+        l0 = obj.launch_count
+        v = obj.n2LL(theta)
+        assert obj.launch_count - l0 <= 6
+        assert abs(v - o.n2ll(theta, D, X, W, y, cov, profile=True)) <= TOL_N2LL * abs(v)
+
+
+@pytest.mark.parametrize("n,n_new,p,cov,taper", [(400, 7, 2, "exp", None), (1500, 300, 3, "mat52", None),
+                                                 (1200, 150, 2, "exp", 1.0)])
+def test_predict_matches_reference_eblup(n, n_new, p, cov, taper):
+    o = _oracle()
+    from varycoef_b200 import SVCObjective
+    locs, X, W, y = synth(n, p, 77 + n, 2)
+    rng = np.random.default_rng(3)
+    newlocs = rng.uniform(locs.min(), locs.max(), (n_new, 2))
+    newX = np.column_stack([np.ones(n_new), rng.standard_normal((n_new, p - 1))])
+    theta = theta_for(p)
+    mu = np.arange(1, p + 1) * 0.9
+    with SVCObjective(y, X, locs, cov_name=cov, tapering=taper) as obj:
+        pr = obj.predict(theta, mu, newlocs, newX, newX, compute_y_var=True)
+        ref = o.predict(theta, mu, locs, X, W, y, newlocs, newX, newX, cov, taper, compute_y_var=True)
+        assert np.allclose(pr["eff"], ref["eff"], rtol=1e-8, atol=1e-10)
+        assert np.allclose(pr["y_pred"], ref["y_pred"], rtol=1e-9, atol=1e-10)
+        assert np.allclose(pr["y_var"], ref["y_var"], rtol=1e-7, atol=1e-9)
+        # fitted values: newlocs = NULL -> the training locations (fitted_computation, R-pkg/R/SVC_mle.R:245-251)
+        fit = obj.predict(theta, mu, None, X, W)
+        reff = o.predict(theta, mu, locs, X, W, y, None, X, W, cov, taper)
+        assert np.allclose(fit["y_pred"], reff["y_pred"], rtol=1e-9, atol=1e-10)
+
+
+def test_vignette_fitted_rows_on_gpu(vignette_train, golden):
+    """head(fitted(fit_svc)) of examples/01_Introduction.html from the printed estimates."""
+    from varycoef_b200 import SVCObjective
+    y, X, locs = vignette_train
+    with SVCObjective(y, X, locs) as obj:
+        pr = obj.predict(np.array(golden["cov_par"]), np.array(golden["coef"]), None, X, X)
+    f = golden["fitted_head"]
+    assert np.allclose(pr["eff"][:6, 0], f["SVC_1"], atol=2e-5)
+    assert np.allclose(pr["eff"][:6, 1], f["SVC_2"], atol=2e-5)
+    assert np.allclose(pr["y_pred"][:6], f["y_pred"], atol=2e-5)
+    res = y - pr["y_pred"]
+    assert np.allclose(np.quantile(res, [0, 0.25, 0.5, 0.75, 1]), golden["residual_summary"], atol=2e-4)
+
+
+def test_gls_chol_exported_function():
+    """GLS_chol(R, X, y) (R-pkg/R/utils.R:57-101): caller-supplied upper factor, roxygen identity."""
+    o = _oracle()
+    from varycoef_b200 import GLS_chol
+    rng = np.random.default_rng(1)
+    for n in (10, 300, 1111):
+        X = np.column_stack([np.ones(n), 20 + np.arange(1, n + 1)]) if n == 10 else \
+            np.column_stack([np.ones(n), rng.standard_normal((n, 2))])
+        y = rng.standard_normal(n)
+        A = rng.uniform(-1, 1, (n, n))
+        S = A.T @ A + (0 if n == 10 else n * 0.01) * np.eye(n)
+        R = o.chol_upper(S)
+        mu = GLS_chol(R, X, y)
+        ref = np.linalg.solve(X.T @ np.linalg.solve(S, X), X.T @ np.linalg.solve(S, y))
+        assert np.allclose(mu, o.gls_chol(R, X, y), rtol=1e-7)
+        assert np.allclose(mu, ref, rtol=1e-6)
+
+
+def test_full_fit_object_with_fitted_values_and_edof(vignette_train, golden):
+    """SVC_mle with the default control (save.fitted = TRUE): coefficients, logLik, BIC, residual
+    summary and residual standard error as printed by summary(fit_svc) in the vignette."""
+    from varycoef_b200.svc_mle import SVC_mle
+    y, X, locs = vignette_train
+    fit = SVC_mle(y, X, locs)
+    assert round(fit.logLik(), 2) == golden["logLik_2dp"]
+    assert fit.df["df"] == 4
+    assert np.isfinite(fit.df["edof"]) and 4 < fit.df["edof"] < 100
+    assert np.allclose(np.quantile(fit.residuals, [0, 0.25, 0.5, 0.75, 1]), golden["residual_summary"], atol=5e-3)
+    o = _oracle()
+    D = o.own_dist(locs)
+    assert fit.df["edof"] == pytest.approx(o.eff_dof(fit.cov_par, X, o.sigma_y(fit.cov_par, D, X)), rel=1e-8)

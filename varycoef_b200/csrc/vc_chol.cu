@@ -447,6 +447,7 @@ constexpr int POTRFB_SMEM = ((TILE + 1) * PLD + TILE + 8 * PB * SS_LD) * (int)si
 
 __device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 
+template <bool FACTOR>   // FACTOR = false: the tile already holds L; only invert it (vc_gls_chol)
 __global__ void __launch_bounds__(POTRF_THREADS, 1)
 k_potrf128b(double* __restrict__ At, int64_t lda, int jt, double* __restrict__ linv_all,
             double* __restrict__ logdet_part, int* __restrict__ info) {
@@ -474,6 +475,13 @@ k_potrf128b(double* __restrict__ At, int64_t lda, int jt, double* __restrict__ l
 #pragma unroll
       for (int j = 0; j < PB; ++j) {
         const double ajj = shfl_d(a[j], j);
+        if (!FACTOR) {
+          if (lane == j) {
+            sdiag[k0 + j] = ajj;
+            if (!(ajj > 0.0)) atomicMin(info, jt * TILE + k0 + j + 1);
+          }
+          continue;
+        }
         const double d = sqrt(ajj);
         if (lane == j) {
           sdiag[k0 + j] = d;
@@ -513,7 +521,7 @@ k_potrf128b(double* __restrict__ At, int64_t lda, int jt, double* __restrict__ l
     __syncthreads();
     const int nsub = (TILE - k0 - PB) / 8;   // 8-row sub-tiles below the diagonal block
     // ---- B: panel solve  P = A * Dinv^T  on rows [k0+16, 128) ----
-    for (int ms = warp; ms < nsub; ms += 8) {
+    for (int ms = warp; FACTOR && ms < nsub; ms += 8) {
       const int row0 = k0 + PB + 8 * ms;
       double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
 #pragma unroll
@@ -537,7 +545,7 @@ k_potrf128b(double* __restrict__ At, int64_t lda, int jt, double* __restrict__ l
     __syncthreads();
     // ---- C: trailing update on the lower triangle of 8x8 sub-tiles ----
     const int npair = nsub * (nsub + 1) / 2;
-    for (int t = warp; t < npair; t += 8) {
+    for (int t = warp; FACTOR && t < npair; t += 8) {
       int sa = (int)((sqrtf(8.0f * t + 1.0f) - 1.0f) * 0.5f);
       while ((sa + 1) * (sa + 2) / 2 <= t) ++sa;
       while (sa * (sa + 1) / 2 > t) --sa;
@@ -632,7 +640,7 @@ k_potrf128b(double* __restrict__ At, int64_t lda, int jt, double* __restrict__ l
   double* linv = linv_all + (int64_t)jt * TILE * TILE;
   for (int idx = tid; idx < TILE * TILE; idx += POTRF_THREADS) {
     const int r = idx & (TILE - 1), c = idx >> 7;
-    if (r >= c) At[r + (int64_t)c * lda] = M[c * PLD + r];
+    if (FACTOR && r >= c) At[r + (int64_t)c * lda] = M[c * PLD + r];
     linv[idx] = (r >= c) ? M[(r + 1) * PLD + c] : 0.0;
   }
   if (tid < 32) {
@@ -681,10 +689,11 @@ void append_trapezoid(std::vector<int>& out, int J0, int J1, int nrows) {
         }
       }
 }
-// border rows only: I in [nt, nrows), J in [J0, J1)
-void append_border(std::vector<int>& out, int J0, int J1, int nt, int nrows) {
+// border rows only: I in [nt, nrows), J in [J0, J1).  ib_lim: border tiles ib >= ib_lim are still
+// exactly zero in the panel columns of this step (identity-structured right-hand sides) and are skipped.
+void append_border(std::vector<int>& out, int J0, int J1, int nt, int nrows, int ib_lim) {
   for (int J = J0; J < J1; ++J)
-    for (int I = nt; I < nrows; ++I) out.push_back(I | (J << 16));
+    for (int I = nt; I < nrows && I - nt < ib_lim; ++I) out.push_back(I | (J << 16));
 }
 
 void build_plan(VcCholPlan& pl, int nt, int nbt, int nb, bool lookahead, int mode) {
@@ -698,7 +707,7 @@ void build_plan(VcCholPlan& pl, int nt, int nbt, int nb, bool lookahead, int mod
     c.k0 = k0; c.K = K; c.tile_off = (int64_t)tiles.size();
     if (J1 > J0) {
       if (mode == VC_SWEEP_FACTOR) append_trapezoid(tiles, J0, J1, nrows);
-      else append_border(tiles, J0, J1, nt, nrows);
+      else append_border(tiles, J0, J1, nt, nrows, mode == VC_SWEEP_SOLVE_IDENT ? (k0 + K) / TILE : INT_MAX);
     }
     c.ntiles = (int)((int64_t)tiles.size() - c.tile_off);
     pl.calls.push_back(c);
@@ -741,8 +750,19 @@ void vc_chol_init() {
   VC_CUDA_TRY(cudaFuncSetAttribute(k_syrk_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
   VC_CUDA_TRY(cudaFuncSetAttribute(k_syrk_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM));
   VC_CUDA_TRY(cudaFuncSetAttribute(k_potrf128, cudaFuncAttributeMaxDynamicSharedMemorySize, POTRF_SMEM));
-  VC_CUDA_TRY(cudaFuncSetAttribute(k_potrf128b, cudaFuncAttributeMaxDynamicSharedMemorySize, POTRFB_SMEM));
+  VC_CUDA_TRY(cudaFuncSetAttribute(k_potrf128b<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, POTRFB_SMEM));
+  VC_CUDA_TRY(cudaFuncSetAttribute(k_potrf128b<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, POTRFB_SMEM));
   done = true;
+}
+
+// inverse of every diagonal tile of a factor that is already resident (no factorisation)
+void vc_chol_invert_diag_tiles(const VcMatrix& M, VcCholWork& w, int64_t* launches) {
+  vc_launch_reset_info(w.info, w.st_main, launches);
+  for (int jt = 0; jt < M.nt; ++jt) {
+    double* diag = M.a + (int64_t)jt * TILE * (M.lda + 1);
+    k_potrf128b<false><<<1, POTRF_THREADS, POTRFB_SMEM, w.st_main>>>(diag, M.lda, jt, w.linv, w.logdet_part, w.info);
+    ++*launches;
+  }
 }
 
 void vc_chol_free_plans(VcCholWork& w) {
@@ -755,7 +775,7 @@ void vc_chol_free_plans(VcCholWork& w) {
 void vc_launch_potrf(double* diag, int64_t lda, int jt, double* linv_all, double* logdet_part, int* info,
                      bool legacy, cudaStream_t st, int64_t* launches) {
   if (legacy) k_potrf128<<<1, POTRF_THREADS, POTRF_SMEM, st>>>(diag, lda, jt, linv_all, logdet_part, info);
-  else k_potrf128b<<<1, POTRF_THREADS, POTRFB_SMEM, st>>>(diag, lda, jt, linv_all, logdet_part, info);
+  else k_potrf128b<true><<<1, POTRF_THREADS, POTRFB_SMEM, st>>>(diag, lda, jt, linv_all, logdet_part, info);
   ++*launches;
 }
 void vc_launch_trsm(const VcGemmArgs& g, int grid, cudaStream_t st, int64_t* launches) {
@@ -824,9 +844,10 @@ static int pick_reserved_sms(int num_sms, int rows_t /*row tiles below the panel
 // stored diagonal inverses) and sweeps only the border rows: a blocked forward substitution.
 void vc_chol_factor(const VcMatrix& M, VcCholWork& w, int64_t* launches, int mode) {
   const int nt = M.nt, nbt = M.nbt, nb = w.nb_tiles;
-  const bool solve = (mode == VC_SWEEP_SOLVE);
+  const bool solve = (mode != VC_SWEEP_FACTOR);
   const bool la = w.lookahead && !solve;
   VcCholPlan& pl = solve ? w.plan_solve : w.plan_factor;
+  const bool ident = (mode == VC_SWEEP_SOLVE_IDENT);
   build_plan(pl, nt, nbt, nb, la, mode);
   cudaStream_t sm = w.st_main, sp = la ? w.st_panel : w.st_main;
   if (!solve) {
@@ -847,14 +868,15 @@ void vc_chol_factor(const VcMatrix& M, VcCholWork& w, int64_t* launches, int mod
         if (w.legacy_potrf)
           k_potrf128<<<1, POTRF_THREADS, POTRF_SMEM, sp>>>(diag, M.lda, jt, w.linv, w.logdet_part, w.info);
         else
-          k_potrf128b<<<1, POTRF_THREADS, POTRFB_SMEM, sp>>>(diag, M.lda, jt, w.linv, w.logdet_part, w.info);
+          k_potrf128b<true><<<1, POTRF_THREADS, POTRFB_SMEM, sp>>>(diag, M.lda, jt, w.linv, w.logdet_part, w.info);
         ++*launches;
       }
       GemmArgs g = base_args(M);
       g.linv = w.linv + (int64_t)jt * TILE * TILE;
       g.k0 = jt * TILE; g.K = TILE; g.jt = jt;
       g.n_main = solve ? 0 : nt - (jt + 1);
-      const int grid = g.n_main + nbt;
+      // identity-structured borders: tile ib is still zero in columns < 128 ib
+      const int grid = g.n_main + (ident ? std::min(nbt, jt + 1) : nbt);
       if (grid > 0) {
         k_trsm_panel<<<grid, GEMM_THREADS, GEMM_SMEM, sp>>>(g);
         ++*launches;

@@ -129,10 +129,12 @@ struct VcCholWork {
   VcCholPlan plan_factor, plan_solve;
 };
 enum { VC_SWEEP_FACTOR = 0,   // potrf + TRSM + updates on every row tile (main + border)
-       VC_SWEEP_SOLVE = 1 };  // factor already resident: only the border rows are swept
+       VC_SWEEP_SOLVE = 1,    // factor already resident: only the border rows are swept
+       VC_SWEEP_SOLVE_IDENT = 2 };  // same, border = identity rows: tiles known to be zero are skipped
 void vc_chol_init();
 void vc_chol_factor(const VcMatrix& M, VcCholWork& w, int64_t* launches, int mode = VC_SWEEP_FACTOR);
 void vc_chol_free_plans(VcCholWork& w);
+void vc_chol_invert_diag_tiles(const VcMatrix& M, VcCholWork& w, int64_t* launches);
 // raw launchers (used by the distributed driver, vc_dist.cu)
 void vc_launch_potrf(double* diag, int64_t lda, int jt, double* linv_all, double* logdet_part, int* info,
                      bool legacy, cudaStream_t st, int64_t* launches);
