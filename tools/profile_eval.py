@@ -22,9 +22,10 @@ y = X @ np.array([1.0, 2.0, 0.5]) + rng.standard_normal(n) * 1.8
 theta = np.array([1.3, 0.7, 2.1, 0.4, 0.9, 1.1, 0.35])
 obj = SVCObjective(y, X, locs, profileLik=True, nb_outer=nb, lookahead=la, legacy_syrk=legacy, legacy_potrf=legacy_potrf)
 v = obj.n2LL(theta)
-for _ in range(reps):
+for rep in range(reps):
+    th = theta * (1.0 + 1e-3 * (rep + 1))      # a new theta every time: no factor-cache hit
     t0 = time.time()
-    v = obj.n2LL(theta)
+    v = obj.n2LL(th)
     dt = time.time() - t0
     tm = obj.timings()
     print("legacy=%d lp=%d " % (legacy, legacy_potrf), end="")
