@@ -442,7 +442,7 @@ k_potrf128(double* __restrict__ At, int64_t lda, int jt, double* __restrict__ li
 constexpr int PLD = 132;
 constexpr int PB = 16;
 constexpr int SS_LD = 20;   // per-warp 16x16 scratch, column stride 20 doubles
-constexpr int POTRFB_SMEM = ((TILE + 1) * PLD + TILE + 8 * PB * SS_LD) * (int)sizeof(double);
+constexpr int POTRFB_SMEM = ((TILE + 1) * PLD + TILE + 8 * PB * SS_LD + 2 * PB * 17) * (int)sizeof(double);
 
 __device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 
@@ -453,6 +453,8 @@ k_potrf128b(double* __restrict__ At, int64_t lda, int jt, double* __restrict__ l
   extern __shared__ __align__(16) double M[];
   double* sdiag = M + (TILE + 1) * PLD;
   double* scratch = sdiag + TILE;
+  double* Dsh = scratch + 8 * PB * SS_LD;   // 16 x 17
+  double* Xsh = Dsh + PB * 17;
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, tig = lane & 3;
@@ -465,56 +467,43 @@ k_potrf128b(double* __restrict__ At, int64_t lda, int jt, double* __restrict__ l
 
   for (int kb = 0; kb < TILE / PB; ++kb) {
     const int k0 = kb * PB;
-    // ---- A: diagonal 16x16 block, factor + inverse, warp 0, lane r < 16 owns row r ----
-    if (warp == 0) {
-      const int r = lane & 15;
-      double a[PB], x[PB];
-#pragma unroll
-      for (int k = 0; k < PB; ++k) a[k] = (k <= r) ? M[(k0 + k) * PLD + k0 + r] : 0.0;
-#pragma unroll
-      for (int j = 0; j < PB; ++j) {
-        const double ajj = shfl_d(a[j], j);
-        if (!FACTOR) {
-          if (lane == j) {
-            sdiag[k0 + j] = ajj;
-            if (!(ajj > 0.0)) atomicMin(info, jt * TILE + k0 + j + 1);
+    // ---- A: diagonal 16x16 block, factor + inverse; thread (i, j) owns element (i, j) ----
+    {
+      const int i = tid & 15, j = tid >> 4;
+      Dsh[i * 17 + j] = (i >= j) ? M[(k0 + j) * PLD + k0 + i] : 0.0;
+      Xsh[i * 17 + j] = (i == j) ? 1.0 : 0.0;
+      __syncthreads();
+      for (int jj = 0; jj < PB; ++jj) {
+        const double ajj = Dsh[jj * 17 + jj];              // final: columns < jj were applied before the barrier
+        if (FACTOR) {
+          // the pivot element itself is left untouched inside the loop (sqrt goes to sdiag), so one
+          // barrier per phase is enough: scale column jj | barrier | rank-1 update | barrier
+          if (j == jj && i > jj) Dsh[i * 17 + jj] *= 1.0 / sqrt(ajj);
+          if (tid == jj * 17) {                              // thread (jj, jj)
+            sdiag[k0 + jj] = sqrt(ajj);
+            if (!(ajj > 0.0)) atomicMin(info, jt * TILE + k0 + jj + 1);
           }
-          continue;
-        }
-        const double d = sqrt(ajj);
-        if (lane == j) {
-          sdiag[k0 + j] = d;
-          if (!(ajj > 0.0)) atomicMin(info, jt * TILE + k0 + j + 1);
-        }
-        const double dinv = 1.0 / d;
-        if (r == j) a[j] = d;
-        else if (r > j) a[j] *= dinv;
-#pragma unroll
-        for (int k = j + 1; k < PB; ++k) {
-          const double lkj = shfl_d(a[j], k);
-          if (r >= k) a[k] = fma(-a[j], lkj, a[k]);
+          __syncthreads();
+          if (j > jj && i >= j) Dsh[i * 17 + j] = fma(-Dsh[i * 17 + jj], Dsh[j * 17 + jj], Dsh[i * 17 + j]);
+          __syncthreads();
+        } else if (tid == jj * 17) {
+          sdiag[k0 + jj] = ajj;
+          if (!(ajj > 0.0)) atomicMin(info, jt * TILE + k0 + jj + 1);
         }
       }
-      // inverse: lane c builds column c of D^-1 by forward substitution
-      const int c = r;
-#pragma unroll
-      for (int i = 0; i < PB; ++i) {
-        double sacc = (i == c) ? 1.0 : 0.0;
-#pragma unroll
-        for (int k = 0; k < i; ++k) {
-          const double dik = shfl_d(a[k], i);
-          if (k >= c) sacc = fma(-dik, x[k], sacc);
-        }
-        const double dii = shfl_d(a[i], i);
-        x[i] = (i >= c) ? sacc / dii : 0.0;
+      __syncthreads();
+      if (FACTOR && i == j) Dsh[i * 17 + i] = sdiag[k0 + i];
+      __syncthreads();
+      // X = D^-1, right-looking forward substitution on the identity (element (i, c = j))
+      for (int k = 0; k < PB; ++k) {
+        if (i == k) Xsh[k * 17 + j] *= 1.0 / Dsh[k * 17 + k];
+        __syncthreads();
+        if (i > k) Xsh[i * 17 + j] = fma(-Dsh[i * 17 + k], Xsh[k * 17 + j], Xsh[i * 17 + j]);
+        __syncthreads();
       }
-      if (lane < PB) {
-#pragma unroll
-        for (int k = 0; k < PB; ++k)
-          if (k <= r) M[(k0 + k) * PLD + k0 + r] = a[k];
-#pragma unroll
-        for (int i = 0; i < PB; ++i)
-          if (i >= c) M[(k0 + i + 1) * PLD + k0 + c] = x[i];
+      if (i >= j) {
+        if (FACTOR) M[(k0 + j) * PLD + k0 + i] = Dsh[i * 17 + j];
+        M[(k0 + i + 1) * PLD + k0 + j] = Xsh[i * 17 + j];
       }
     }
     __syncthreads();
@@ -807,11 +796,12 @@ static GemmArgs base_args(const VcMatrix& M) {
 }
 
 static void launch_update(const VcMatrix& M, const VcCholWork& w, const VcCholPlan& pl, size_t call,
-                          cudaStream_t st, int64_t* launches, int reserve_sms = 0) {
+                          cudaStream_t st, int64_t* launches, int reserve_sms = 0, int first = 0, int count = -1) {
   const VcUpdateCall& c = pl.calls[call];
-  if (c.ntiles == 0) return;
+  if (count < 0) count = c.ntiles - first;
+  if (count <= 0) return;
   GemmArgs g = base_args(M);
-  g.k0 = c.k0; g.K = c.K; g.tiles = pl.tiles_dev + c.tile_off; g.ntiles = c.ntiles;
+  g.k0 = c.k0; g.K = c.K; g.tiles = pl.tiles_dev + c.tile_off + first; g.ntiles = count;
   vc_launch_syrk(g, w.num_sms - reserve_sms, w.legacy_syrk, st, launches);
 }
 
@@ -819,28 +809,30 @@ static void launch_update(const VcMatrix& M, const VcCholWork& w, const VcCholPl
 // (other stream) only overlaps if some SMs are left free.  Pick the number R of SMs to leave to the
 // panel so that max(panel time on R SMs, trailing update on num_sms - R SMs) is smallest.
 static int pick_reserved_sms(int num_sms, int rows_t /*row tiles below the panel*/, int nb,
-                             int rest_tiles) {
+                             int rest_tiles, int* tiles_beside_panel) {
+  *tiles_beside_panel = rest_tiles;
   if (rest_tiles <= 0) return 0;
-  const double t_potrf = 60.0, t_tile128 = 20.0, t_tile_nb = 17.0 * nb;   // microseconds
-  const double panel_serial = nb * t_potrf;
+  const double t_potrf = 45.0, t_tile128 = 20.0, t_tile_nb = 17.0 * nb;   // microseconds
+  const double panel_serial = nb * (t_potrf + 2 * t_tile128);
   const double panel_par = (nb + nb * (nb - 1) / 2.0) * rows_t * t_tile128;
-  int best = 0;
-  double best_t = 1e300;
+  int best = 1;
+  double best_t = 1e300, best_tp = 0.0;
   for (int r = 1; r <= num_sms / 2; ++r) {
     const double tp = panel_serial + panel_par / r;
     const double tu = (double)((rest_tiles + (num_sms - r) - 1) / (num_sms - r)) * t_tile_nb;
     const double t = std::max(tp, tu);
-    if (t < best_t) { best_t = t; best = r; }
+    if (t < best_t) { best_t = t; best = r; best_tp = tp; }
+  }
+  // Only the part of the update that overlaps the panel needs to leave SMs free: run twice the
+  // panel's estimated duration on num_sms - R CTAs, the remainder on the full machine afterwards.
+  const double waves = 2.0 * best_tp / t_tile_nb;
+  const double tiles = waves * (num_sms - best);
+  if (tiles < 0.7 * rest_tiles) {
+    int nA = (int)(tiles / (num_sms - best) + 1.0) * (num_sms - best);
+    *tiles_beside_panel = std::min(nA, rest_tiles);
   }
   return best;
 }
-
-// Sweep the bordered matrix.  Two-level blocking: 128-wide sub-panels (potrf128 + TRSM-as-GEMM +
-// inner update of the rest of the outer block, K = 128) inside nb-wide outer blocks whose
-// trailing SYRK runs with K = nb.  With lookahead the next outer block's columns are updated
-// first and its panel is factored on a second (high-priority) stream while the rest of the
-// trailing matrix is still being updated.  mode VC_SWEEP_SOLVE reuses a resident factor (and the
-// stored diagonal inverses) and sweeps only the border rows: a blocked forward substitution.
 void vc_chol_factor(const VcMatrix& M, VcCholWork& w, int64_t* launches, int mode) {
   const int nt = M.nt, nbt = M.nbt, nb = w.nb_tiles;
   const bool solve = (mode != VC_SWEEP_FACTOR);
@@ -857,53 +849,68 @@ void vc_chol_factor(const VcMatrix& M, VcCholWork& w, int64_t* launches, int mod
     VC_CUDA_TRY(cudaEventRecord(w.ev_update, sm));
     VC_CUDA_TRY(cudaStreamWaitEvent(sp, w.ev_update, 0));
   }
-  size_t call = 0;
-  for (int ob = 0; ob < nt; ob += nb) {
+  // plan call index of the first inner update of every outer block (mirrors build_plan)
+  std::vector<size_t> first_call;
+  {
+    size_t c = 0;
+    for (int ob = 0; ob < nt; ob += nb) {
+      const int oe = std::min(ob + nb, nt);
+      first_call.push_back(c);
+      c += (size_t)(oe - ob);
+      if (oe < nt) c += la ? 2 : 1;
+    }
+  }
+  auto panel = [&](int ob) {   // potrf / TRSM / inner update of every 128-wide sub-panel of block ob
     const int oe = std::min(ob + nb, nt);
-    // ---- panel: columns [ob, oe) on the panel stream ----
+    size_t call = first_call[ob / nb];
     for (int jt = ob; jt < oe; ++jt) {
       if (!solve) {
         double* diag = M.a + (int64_t)jt * TILE * (M.lda + 1);
-        if (w.legacy_potrf)
-          k_potrf128<<<1, POTRF_THREADS, POTRF_SMEM, sp>>>(diag, M.lda, jt, w.linv, w.logdet_part, w.info);
-        else
-          k_potrf128b<true><<<1, POTRF_THREADS, POTRFB_SMEM, sp>>>(diag, M.lda, jt, w.linv, w.logdet_part, w.info);
-        ++*launches;
+        vc_launch_potrf(diag, M.lda, jt, w.linv, w.logdet_part, w.info, w.legacy_potrf, sp, launches);
       }
       GemmArgs g = base_args(M);
       g.linv = w.linv + (int64_t)jt * TILE * TILE;
       g.k0 = jt * TILE; g.K = TILE; g.jt = jt;
       g.n_main = solve ? 0 : nt - (jt + 1);
       // identity-structured borders: tile ib is still zero in columns < 128 ib
-      const int grid = g.n_main + (ident ? std::min(nbt, jt + 1) : nbt);
-      if (grid > 0) {
-        k_trsm_panel<<<grid, GEMM_THREADS, GEMM_SMEM, sp>>>(g);
-        ++*launches;
-      }
+      vc_launch_trsm(g, g.n_main + (ident ? std::min(nbt, jt + 1) : nbt), sp, launches);
       launch_update(M, w, pl, call++, sp, launches);
     }
+  };
+  if (!la) {
+    for (int ob = 0; ob < nt; ob += nb) {
+      const int oe = std::min(ob + nb, nt);
+      panel(ob);
+      if (oe < nt) launch_update(M, w, pl, first_call[ob / nb] + (size_t)(oe - ob), sm, launches);
+    }
+    return;
+  }
+  // Lookahead, software-pipelined over the outer blocks:
+  //   sm:  col(s) | rest A(s) on num_sms - R CTAs ............ | rest B(s) on every SM | col(s+1) ...
+  //   sp:          panel(s+1): potrf / TRSM / inner updates ---^ (rest B and col(s+1) wait for it)
+  // The next panel only touches columns [oe, ne), which the rest update neither reads nor writes.
+  panel(0);
+  VC_CUDA_TRY(cudaEventRecord(w.ev_panel, sp));
+  for (int ob = 0; ob < nt; ob += nb) {
+    const int oe = std::min(ob + nb, nt);
     if (oe >= nt) break;
-    if (!la) {
-      launch_update(M, w, pl, call++, sm, launches);
-    } else {
-      // panel [ob, oe) is final on sp; main stream waits for it
-      VC_CUDA_TRY(cudaEventRecord(w.ev_panel, sp));
+    const size_t c_col = first_call[ob / nb] + (size_t)(oe - ob), c_rest = c_col + 1;
+    VC_CUDA_TRY(cudaStreamWaitEvent(sm, w.ev_panel, 0));
+    launch_update(M, w, pl, c_col, sm, launches);
+    VC_CUDA_TRY(cudaEventRecord(w.ev_col, sm));
+    VC_CUDA_TRY(cudaStreamWaitEvent(sp, w.ev_col, 0));
+    const int rest_tiles = pl.calls[c_rest].ntiles;
+    int nA = rest_tiles;
+    const int reserve = w.legacy_syrk ? 0 : pick_reserved_sms(w.num_sms, nt + nbt - oe, nb, rest_tiles, &nA);
+    launch_update(M, w, pl, c_rest, sm, launches, reserve, 0, nA);
+    panel(oe);
+    VC_CUDA_TRY(cudaEventRecord(w.ev_panel, sp));
+    if (nA < rest_tiles) {
       VC_CUDA_TRY(cudaStreamWaitEvent(sm, w.ev_panel, 0));
-      // next panel's columns first ...
-      launch_update(M, w, pl, call++, sm, launches);
-      VC_CUDA_TRY(cudaEventRecord(w.ev_col, sm));
-      // ... then the rest of the trailing matrix, overlapping the next panel on sp.  The next
-      // panel only touches columns [oe, ne), which the rest update neither reads nor writes.
-      const int rest_tiles = pl.calls[call].ntiles;
-      const int reserve = w.legacy_syrk ? 0 : pick_reserved_sms(w.num_sms, nt + nbt - oe, nb, rest_tiles);
-      launch_update(M, w, pl, call++, sm, launches, reserve);
-      VC_CUDA_TRY(cudaStreamWaitEvent(sp, w.ev_col, 0));
+      launch_update(M, w, pl, c_rest, sm, launches, 0, nA, rest_tiles - nA);
     }
   }
-  if (la) {
-    VC_CUDA_TRY(cudaEventRecord(w.ev_panel, sp));
-    VC_CUDA_TRY(cudaStreamWaitEvent(sm, w.ev_panel, 0));
-  }
+  VC_CUDA_TRY(cudaStreamWaitEvent(sm, w.ev_panel, 0));
 }
 
 // ---------------------------------------------------------------------------------------------
