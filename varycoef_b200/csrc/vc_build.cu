@@ -162,6 +162,115 @@ __global__ void __launch_bounds__(BUILD_THREADS) k_build(BuildArgs p) {
   }
 }
 
+
+// Fast path of K1: Euclidean distance, D <= 3 coordinate columns, Q <= 4 SVCs, everything a
+// compile-time constant (no per-term predicates, row operands in registers, two columns in flight
+// per thread for instruction-level parallelism).  Same arithmetic as k_build.
+template <int COV, int D, int Q>
+__global__ void __launch_bounds__(BUILD_THREADS, 3) k_build_fast(BuildArgs p) {
+  __shared__ __align__(16) double tab[VC_EXP_TABLE_SIZE];
+  __shared__ __align__(16) double colX[D][TILE];
+  __shared__ __align__(16) double colW[Q][TILE];
+  int I, J;
+  if (p.tiles) {
+    const int packed = p.tiles[blockIdx.x];
+    I = packed & 0xffff;
+    J = packed >> 16;
+  } else {
+    const int id = blockIdx.x;
+    I = (int)((sqrt(8.0 * id + 1.0) - 1.0) * 0.5);
+    while ((I + 1) * (I + 2) / 2 <= id) ++I;
+    while (I * (I + 1) / 2 > id) --I;
+    J = id - I * (I + 1) / 2;
+  }
+  const int tid = threadIdx.x;
+  if (tid < VC_EXP_TABLE_SIZE) tab[tid] = c_exp2_tab[tid];
+  for (int idx = tid; idx < D * TILE; idx += BUILD_THREADS)
+    colX[idx / TILE][idx % TILE] = p.locs[(int64_t)(idx / TILE) * p.n_pad + (int64_t)J * TILE + idx % TILE];
+  for (int idx = tid; idx < Q * TILE; idx += BUILD_THREADS)
+    colW[idx / TILE][idx % TILE] = p.w[(int64_t)(idx / TILE) * p.n_pad + (int64_t)J * TILE + idx % TILE];
+  const int rg = tid & 63, cg = tid >> 6;
+  const int r0 = 2 * rg;
+  const int64_t gi0 = (int64_t)I * TILE + r0;
+  double xi0[D], xi1[D], wi0[Q], wi1[Q], ir[Q], sk[Q];
+#pragma unroll
+  for (int c = 0; c < D; ++c) {
+    const double2 v = *reinterpret_cast<const double2*>(p.locs + (int64_t)c * p.n_pad + gi0);
+    xi0[c] = v.x; xi1[c] = v.y;
+  }
+#pragma unroll
+  for (int k = 0; k < Q; ++k) {
+    const double2 v = *reinterpret_cast<const double2*>(p.w + (int64_t)k * p.n_pad + gi0);
+    wi0[k] = v.x; wi1[k] = v.y;
+    ir[k] = p.th.inv_range[k];
+    sk[k] = p.th.sill[k];
+  }
+  const int lI = p.blk ? ((I / p.blk) / p.pr) * p.blk + I % p.blk : I;
+  const int lJ = p.blk ? ((J / p.blk) / p.pc) * p.blk + J % p.blk : J;
+  double* out = p.out + (int64_t)lI * TILE + r0 + (int64_t)lJ * TILE * p.ld;
+  const int taper_id = p.th.taper_id;
+  const double inv_delta = p.th.inv_delta;
+  __syncthreads();
+#pragma unroll 2
+  for (int cc = 0; cc < 32; ++cc) {
+    const int j = cg * 32 + cc;
+    const int64_t gj = (int64_t)J * TILE + j;
+    double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+    for (int c = 0; c < D; ++c) {
+      const double xj = colX[c][j];
+      const double d0 = xi0[c] - xj, d1 = xi1[c] - xj;
+      s0 = fma(d0, d0, s0);
+      s1 = fma(d1, d1, s1);
+    }
+    const double h0 = sqrt(s0), h1 = sqrt(s1);
+    double v0 = 0.0, v1 = 0.0;
+#pragma unroll
+    for (int k = 0; k < Q; ++k) {
+      const double wj = colW[k][j];
+      v0 = fma(wi0[k] * wj, sk[k] * vc_cov_shape<COV>(h0 * ir[k], tab), v0);
+      v1 = fma(wi1[k] * wj, sk[k] * vc_cov_shape<COV>(h1 * ir[k], tab), v1);
+    }
+    if (taper_id != VC_TAPER_NONE) {
+      v0 *= vc_taper(taper_id, h0, inv_delta);
+      v1 *= vc_taper(taper_id, h1, inv_delta);
+    }
+    if (gi0 == gj) v0 += (gj < p.n) ? p.th.tau2 : 1.0;
+    if (gi0 + 1 == gj) v1 += (gj < p.n) ? p.th.tau2 : 1.0;
+    *reinterpret_cast<double2*>(out + (int64_t)j * p.ld) = make_double2(v0, v1);
+  }
+}
+
+template <int COV, int D>
+bool launch_fast_q(const BuildArgs& a, unsigned grid, cudaStream_t st) {
+  switch (a.th.q) {
+    case 1: k_build_fast<COV, D, 1><<<grid, BUILD_THREADS, 0, st>>>(a); return true;
+    case 2: k_build_fast<COV, D, 2><<<grid, BUILD_THREADS, 0, st>>>(a); return true;
+    case 3: k_build_fast<COV, D, 3><<<grid, BUILD_THREADS, 0, st>>>(a); return true;
+    case 4: k_build_fast<COV, D, 4><<<grid, BUILD_THREADS, 0, st>>>(a); return true;
+    default: return false;
+  }
+}
+template <int COV>
+bool launch_fast_d(const BuildArgs& a, unsigned grid, cudaStream_t st) {
+  switch (a.d) {
+    case 1: return launch_fast_q<COV, 1>(a, grid, st);
+    case 2: return launch_fast_q<COV, 2>(a, grid, st);
+    case 3: return launch_fast_q<COV, 3>(a, grid, st);
+    default: return false;
+  }
+}
+// exp / Matern with Euclidean distances, d <= 3, q <= 4: the common case of the reference's API
+bool launch_fast(const BuildArgs& a, unsigned grid, cudaStream_t st) {
+  if (a.th.dist_method != VC_DIST_EUCLIDEAN) return false;
+  switch (a.th.cov_id) {
+    case VC_COV_EXP: return launch_fast_d<0>(a, grid, st);
+    case VC_COV_MAT32: return launch_fast_d<1>(a, grid, st);
+    case VC_COV_MAT52: return launch_fast_d<2>(a, grid, st);
+    default: return false;
+  }
+}
+
 template <bool FULL>
 void launch_build_t(const BuildArgs& a, cudaStream_t st, unsigned grid_override = 0) {
   const int d = a.d, q = a.th.q;
@@ -169,6 +278,7 @@ void launch_build_t(const BuildArgs& a, cudaStream_t st, unsigned grid_override 
   const size_t smem = (VC_EXP_TABLE_SIZE + 2 * (size_t)(d + q) * TILE) * sizeof(double);
   const unsigned grid = grid_override ? grid_override
                         : FULL ? (unsigned)a.nt * a.nt : (unsigned)((int64_t)a.nt * (a.nt + 1) / 2);
+  if (!FULL && launch_fast(a, grid, st)) return;
 #define VC_BUILD_CASE(C)                                                               \
   case C:                                                                              \
     if (reg) k_build<C, true, FULL><<<grid, BUILD_THREADS, smem, st>>>(a);             \
