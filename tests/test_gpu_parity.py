@@ -438,3 +438,117 @@ def test_full_fit_object_with_fitted_values_and_edof(vignette_train, golden):
     o = _oracle()
     D = o.own_dist(locs)
     assert fit.df["edof"] == pytest.approx(o.eff_dof(fit.cov_par, X, o.sigma_y(fit.cov_par, D, X)), rel=1e-8)
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE.json configurations as parity cases
+# ---------------------------------------------------------------------------------------------
+def test_config_c1_n1000_exp_fit_dense():
+    """C1: sample_SVCdata-style n = 1000, p = q = 2, exponential; full fit with the default control.
+    The oracle validates the GPU optimum: same value there, vanishing oracle gradient."""
+    o = _oracle()
+    from varycoef_b200.svc_mle import SVC_mle, SVC_mle_control
+    rng = np.random.default_rng(20261019 + 1)
+    n = 1000
+    locs = np.sort(rng.uniform(0, 10, n))            # the package's own 1-D form (R-pkg/R/example.R:56)
+    d = o.sample_svcdata(rng, locs, [2.0, 1.0], [3.0, 1.0], [1.0, 2.0], 0.5, "exp")
+    X, y = d["X"], d["y"]
+    fit = SVC_mle(y, X, locs, control=SVC_mle_control(save_fitted=False), compute_edof=False)
+    assert fit.optim_output["convergence"] == 0
+    D = o.own_dist(locs)
+    par = fit.optim_output["par"]
+    v = o.n2ll(par, D, X, X, y, profile=False, faithful=False)
+    assert abs(v - fit.optim_output["value"]) <= TOL_N2LL * abs(v)
+    # the optimum beats both the starting point and the data-generating parameters (oracle values)
+    truth = np.array([3.0, 2.0, 1.0, 1.0, 0.25, 1.0, 2.0])
+    assert v < o.n2ll(fit.liu["init"], D, X, X, y, profile=False, faithful=False)
+    assert v <= o.n2ll(truth, D, X, X, y, profile=False, faithful=False) + 1e-6
+    assert np.allclose(fit.coef(), [1.0, 2.0], atol=1.5)           # true means, loose
+    assert 0.1 < fit.cov_par[-1] < 0.6                              # true nugget variance 0.25
+
+
+def test_config_c2_n10000_matern32_eval_and_fit():
+    """C2: n = 10 000, p = q = 3, Matern-3/2: one evaluation against the lean oracle, then the full
+    optim fit (profile likelihood, numeric Hessian) on the GPU."""
+    o = _oracle()
+    from varycoef_b200 import SVCObjective
+    from varycoef_b200.svc_mle import SVC_mle, SVC_mle_control
+    import torch
+    n, p = 10000, 3
+    locs, X, W, _ = synth(n, p, 20261019 + 2, 2)
+    # y drawn from the model (sample_SVCdata, R-pkg/R/example.R:98-122): beta_k ~ N(mean_k, Sigma_k), nugget sd 0.5
+    D = o.own_dist(locs)
+    g = torch.Generator(device="cuda").manual_seed(7)
+    true_var, true_scale, true_mean = [2.0, 1.0, 1.5], [3.0, 1.0, 2.0], [1.0, 2.0, 0.5]
+    y = np.zeros(n)
+    Dt = torch.from_numpy(D).cuda()
+    for k in range(p):
+        t = Dt / true_scale[k]
+        Lk = torch.linalg.cholesky(true_var[k] * (1 + t) * torch.exp(-t) + 1e-10 * torch.eye(n, device="cuda", dtype=torch.float64))
+        beta = true_mean[k] + (Lk @ torch.randn(n, 1, device="cuda", dtype=torch.float64, generator=g)).cpu().numpy().ravel()
+        y += beta * X[:, k]
+    del Dt, Lk
+    y += 0.5 * np.random.default_rng(3).standard_normal(n)
+    theta = theta_for(p)
+    with SVCObjective(y, X, locs, cov_name="mat32", profileLik=True) as obj:
+        r = obj.n2LL(theta, parts=True)
+    ref = o.n2ll(theta, D, X, W, y, "mat32", profile=True, faithful=False, parts=True)
+    assert abs(r["n2ll"] - ref["n2ll"]) <= TOL_N2LL * abs(ref["n2ll"])
+    assert _rel(r["mu"], ref["mu"]) <= 1e-9
+    del D
+    # Matern-3/2 at 10 pts / unit^2 is numerically singular for a vanishing nugget (base::chol would
+    # stop with "leading minor not positive" just the same), so the nugget is bounded away from 0
+    liu = {"init": np.array([1.5, 1.0] * p + [1.0]), "lower": np.array([0.05, 0.0] * p + [0.05]),
+           "upper": np.array([20.0, 20.0] * p + [20.0])}
+    ctl = SVC_mle_control(cov_name="mat32", profileLik=True, save_fitted=False, **liu)
+    fit = SVC_mle(y, X, locs, control=ctl, optim_control={"maxit": 40}, compute_edof=False)
+    assert fit.optim_output["convergence"] in (0, 1)
+    assert fit.optim_output["value"] < r["n2ll"]
+    assert np.all(np.isfinite(fit.optim_output["hessian"]))
+    est = fit.cov_par
+    print("C2 fit: theta-hat", np.round(est, 3), "mu-hat", np.round(fit.coef(), 3), fit.optim_output["counts"])
+    assert np.allclose(est[1:6:2], true_var, rtol=0.5)             # variances within 50 % of the truth
+    assert np.allclose(est[0:6:2], true_scale, rtol=0.5)           # ranges
+    assert abs(est[-1] - 0.25) < 0.05                              # nugget variance
+    assert np.allclose(fit.coef(), true_mean, atol=1.0)
+
+
+def test_config_c5_n20000_tapered_dense_on_gpu():
+    """C5: n = 20 000, p = q = 3, exponential with a Wendland-1 taper (delta = 0.6: ~11 neighbours per point in
+    range).  Entries against the spam-semantics oracle on random row blocks, the likelihood against
+    an independent dense factorisation (torch / cuSOLVER) of the GPU-built tapered matrix."""
+    import torch
+    o = _oracle()
+    from varycoef_b200 import SVCObjective
+    n, p, delta = 20000, 3, 0.6
+    locs, X, W, y = synth(n, p, 20261019 + 5, 2)
+    theta = theta_for(p)
+    with SVCObjective(y, X, locs, cov_name="exp", tapering=delta, profileLik=True) as obj:
+        r = obj.n2LL(theta, parts=True)
+        S = obj.Sigma_y(theta)
+    # entries: rows of a few random blocks against the oracle restricted to those rows
+    rng = np.random.default_rng(0)
+    for i0 in rng.integers(0, n - 64, 4):
+        rows = np.arange(i0, i0 + 64)
+        Dr = o._pair_dist(locs[rows], locs)
+        tap = np.where(Dr <= delta, o.cov_func("wend1")(Dr, (delta, 1.0, 0.0)), 0.0)
+        Sr = np.zeros_like(Dr)
+        for k in range(p):
+            Sr += o.cov_func("exp")(Dr, theta[2 * k:2 * k + 2]) * (np.outer(W[rows, k], W[:, k]) * tap)
+        Sr[np.arange(64), rows] += theta[-1]
+        assert _rel(S[rows], Sr) <= TOL_ELEM
+        assert np.all(S[rows][Dr >= delta] == 0.0)
+    frac = np.count_nonzero(S[:2000]) / S[:2000].size
+    assert 3e-4 < frac < 1e-3          # pi delta^2 x density / n = 11.3 neighbours of 20 000
+    St = torch.from_numpy(S).cuda()
+    del S
+    Lt = torch.linalg.cholesky(St)
+    del St
+    logdet = 2.0 * torch.log(torch.diagonal(Lt)).sum().item()
+    Z = torch.linalg.solve_triangular(Lt, torch.from_numpy(np.column_stack([X, y])).cuda(), upper=False)
+    G = (Z.T @ Z).cpu().numpy()
+    mu = np.linalg.solve(G[:p, :p], G[:p, p])
+    rz = Z[:, p] - Z[:, :p] @ torch.from_numpy(mu).cuda()
+    ref = n * np.log(2 * np.pi) + logdet + float((rz @ rz).item())
+    assert abs(r["n2ll"] - ref) <= TOL_N2LL * abs(ref)
+    assert _rel(r["mu"], mu) <= 1e-9
