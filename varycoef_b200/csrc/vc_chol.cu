@@ -302,8 +302,12 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_syrk_ws(GemmArgs p) {
     const int wm = warp & 1, wn = warp >> 1;
     const int g = lane >> 2, tig = lane & 3;
     unsigned it = 0;
+    int packed_next = (blockIdx.x < (unsigned)p.ntiles) ? p.tiles[blockIdx.x] : 0;
     for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
-      const int packed = p.tiles[t];
+      const int packed = packed_next;
+      // the next tile's index is fetched a whole tile ahead: its ~1 us global-load latency would
+      // otherwise sit on the critical path of every tile boundary
+      if (t + (int)gridDim.x < p.ntiles) packed_next = p.tiles[t + gridDim.x];
       const int I = packed & 0xffff, J = packed >> 16;
       int64_t ldc;
       double* Ct = c_tile_ptr(p, I, J, ldc);
