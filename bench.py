@@ -296,14 +296,16 @@ def run_ours(args):
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     hbm_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "6650 GB/s (of fallback)"
-    roof = {"bound": "tensor", "kernel": "k_syrk_update (DMMA trailing SYRK) inside the bordered Cholesky",
+    roof = {"bound": "tensor", "kernel": "k_syrk_ws (persistent TMA-fed DMMA trailing SYRK) inside the bordered Cholesky",
             "achieved": chol_flops / chol_s / 1e12, "peak": peak_tf.value, "unit": "TFLOP/s",
             "frac": chol_flops / chol_s / 1e12 / peak_tf.value if peak_tf.value > 0 else None,
             "traffic": None,
+            "traffic_note": "ncu --set full of one k_syrk_ws launch at n=20k (profiles/r01_syrk_ws_n20k.md): 3.9 GB DRAM "
+                            "for 1.9e11 flop -- 8 % of DRAM peak, DMMA pipe 95.7 % active: compute-bound",
             "peak_source": "fp64 DMMA m8n8k4 register-resident probe measured live on this GPU (vc_probe_dmma_peak); "
                            "MEASURED_PEAKS.json has no fp64 entry",
             "algorithmic": "n^3/3 flops per evaluation / CUDA-event time of the whole factorisation (panels included)"}
-    roof_build = {"bound": "hbm", "kernel": "k_build (fused distance + covariance)", "achieved": build_bytes / build_s / 1e9,
+    roof_build = {"bound": "hbm", "kernel": "k_build_fast (fused distance + covariance)", "achieved": build_bytes / build_s / 1e9,
                   "peak": hbm_peak, "unit": "GB/s", "frac": build_bytes / build_s / 1e9 / hbm_peak,
                   "traffic": None, "peak_source": hbm_src,
                   "algorithmic": "4 n (n+1) bytes written (lower triangle) / CUDA-event time of build + border"}
