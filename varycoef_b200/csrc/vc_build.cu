@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(BUILD_THREADS, 3) k_build_fast(BuildArgs p) {
       s0 = fma(d0, d0, s0);
       s1 = fma(d1, d1, s1);
     }
-    const double h0 = sqrt(s0), h1 = sqrt(s1);
+    const double h0 = vc_sqrt_pos(s0), h1 = vc_sqrt_pos(s1);
     double v0 = 0.0, v1 = 0.0;
 #pragma unroll
     for (int k = 0; k < Q; ++k) {

@@ -55,8 +55,8 @@ VC_HD int32_t vc_double2hiint(double x) {
 // exp(-t) = 2^m * 2^(j/64) * (1 + r + r^2/2 + ... + r^6/720).  About 12 fp64 issue slots
 // against ~30 for the libdevice exp(): the build kernel is fp64-ALU-bound, not HBM-bound.
 VC_HD double vc_exp_neg(double t, const double* __restrict__ tab) {
-  if (!(t < 708.0)) return (t != t) ? t : 0.0;  // exp(-708) = 3e-308: flush below
-  const double x = -t;
+  // branch-free: evaluate on min(t, 708) and select at the end (exp(-708) = 3e-308: flush below)
+  const double x = -fmin(t, 708.0);
   const double kMagic = 6755399441055744.0;          // 2^52 + 2^51
   const double kInv = 92.332482616893656;            // 64 / ln 2
   const double kLn2Hi = 6.93147180369123816490e-01 / 64.0;
@@ -76,7 +76,25 @@ VC_HD double vc_exp_neg(double t, const double* __restrict__ tab) {
   const double tj = tab[ki & (VC_EXP_TABLE_SIZE - 1)];
   double v = fma(tj, p, tj);
   const int32_t m = ki >> VC_EXP_TABLE_BITS;           // arithmetic shift, m in [-1022, 0]
-  return vc_hiloint2double(vc_double2hiint(v) + (m << 20), vc_double2loint(v));
+  v = vc_hiloint2double(vc_double2hiint(v) + (m << 20), vc_double2loint(v));
+  return (t < 708.0) ? v : ((t != t) ? t : 0.0);
+}
+
+// sqrt(s) for s >= 0, <= 1 ulp, branch-free on the device (reciprocal square root seed + two Newton
+// steps + one correction); the libdevice sqrt carries a slow-path call that breaks up the inner loop
+VC_HD double vc_sqrt_pos(double s) {
+#if defined(__CUDA_ARCH__)
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(s));
+  const double hs = 0.5 * s;
+  y = y * fma(-hs * y, y, 1.5);                        // Newton on 1/sqrt(s)
+  y = y * fma(-hs * y, y, 1.5);
+  double h = s * y;
+  h = fma(fma(-h, h, s), 0.5 * y, h);                  // h += (s - h^2) / (2 sqrt(s))
+  return (s > 2.3e-308) ? h : 0.0;
+#else
+  return sqrt(s);
+#endif
 }
 
 // shape(t) = cov(h; range, sill = 1), t = h / range >= 0
