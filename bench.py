@@ -29,6 +29,10 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# NCCL prints its version banner on stdout at the default debug level of this image; the contract
+# is ONE JSON line on stdout, so keep NCCL to warnings unless the caller asked for more
+if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"
 
 WORKLOADS = {
     # name: (n, p=q, cov, taper, seed offset, description)

@@ -812,8 +812,8 @@ static void launch_update(const VcMatrix& M, const VcCholWork& w, const VcCholPl
 // A persistent update kernel keeps every SM it starts on until it is done, so the lookahead panel
 // (other stream) only overlaps if some SMs are left free.  Pick the number R of SMs to leave to the
 // panel so that max(panel time on R SMs, trailing update on num_sms - R SMs) is smallest.
-static int pick_reserved_sms(int num_sms, int rows_t /*row tiles below the panel*/, int nb,
-                             int rest_tiles, int* tiles_beside_panel) {
+int vc_pick_reserved_sms(int num_sms, int rows_t /*row tiles below the panel*/, int nb,
+                         int rest_tiles, int* tiles_beside_panel) {
   *tiles_beside_panel = rest_tiles;
   if (rest_tiles <= 0) return 0;
   const double t_potrf = 45.0, t_tile128 = 20.0, t_tile_nb = 17.0 * nb;   // microseconds
@@ -905,7 +905,7 @@ void vc_chol_factor(const VcMatrix& M, VcCholWork& w, int64_t* launches, int mod
     VC_CUDA_TRY(cudaStreamWaitEvent(sp, w.ev_col, 0));
     const int rest_tiles = pl.calls[c_rest].ntiles;
     int nA = rest_tiles;
-    const int reserve = w.legacy_syrk ? 0 : pick_reserved_sms(w.num_sms, nt + nbt - oe, nb, rest_tiles, &nA);
+    const int reserve = w.legacy_syrk ? 0 : vc_pick_reserved_sms(w.num_sms, nt + nbt - oe, nb, rest_tiles, &nA);
     launch_update(M, w, pl, c_rest, sm, launches, reserve, 0, nA);
     panel(oe);
     VC_CUDA_TRY(cudaEventRecord(w.ev_panel, sp));

@@ -144,6 +144,7 @@ void vc_launch_reset_info(int* info, cudaStream_t st, int64_t* launches);
 void vc_launch_pack_tiles(const VcGemmArgs& g, const int* tiles, int ntiles, int lcol0, int K, double* dst,
                           int tile0, cudaStream_t st, int64_t* launches);
 void vc_append_trapezoid(std::vector<int>& out, int J0, int J1, int nrows);
+int vc_pick_reserved_sms(int num_sms, int rows_t, int nb, int rest_tiles, int* tiles_beside_panel);
 
 // vc_finalize.cu
 struct VcFinalWork {

@@ -349,34 +349,32 @@ int vc_dist_n2ll(vc_handle* h, const double* theta, int32_t mu_mode, const doubl
     // leaves a few SMs to the panel stream and to NCCL's own kernels.
     const bool la = h->cw.lookahead;
     cudaStream_t sm = st, sp = la ? h->st_panel : st;
-    const int reserve = (la && !h->cw.legacy_syrk) ? 8 : 0;
     if (la) {
       VC_CUDA_TRY(cudaEventRecord(h->cw.ev_update, sm));
       VC_CUDA_TRY(cudaStreamWaitEvent(sp, h->cw.ev_update, 0));
     }
-    int sidx = 0;
-    for (const DistStep& s : D->steps) {
+    double* dd_linv = D->dd + (size_t)nb * VC_TILE * ((size_t)nb * VC_TILE);
+    // panel phase of step i (stream sp): diagonal block, L_DD broadcast, column solves, panel broadcast
+    auto panel_phase = [&](size_t i) {
+      const DistStep& s = D->steps[i];
       const int nsub = s.oe - s.ob;
       const int Kb = nsub * VC_TILE;
-      double* pnl = D->pnl[sidx & 1];
-      ++sidx;
-      double* dd_linv = D->dd + (size_t)nb * VC_TILE * ((size_t)nb * VC_TILE);
-      // ---------------- panel phase (stream sp) ----------------
+      double* pnl = D->pnl[i & 1];
       if (D->rank == s.diag_owner) {
         for (int jt = s.ob; jt < s.oe; ++jt) {
-          const int i = jt - s.ob;
+          const int k = jt - s.ob;
           double* diag = h->M.a + (int64_t)loc_tile_h(jt, nb, D->pr) * VC_TILE +
                          (int64_t)loc_tile_h(jt, nb, D->pc) * VC_TILE * h->M.lda;
           // potrf indexes its inverse slot by jt: bias the base so that slot jt is dd_linv[jt - ob]
           vc_launch_potrf(diag, h->M.lda, jt, dd_linv - (int64_t)s.ob * VC_TILE * VC_TILE, h->cw.logdet_part,
                           h->cw.info, h->cw.legacy_potrf, sp, &h->launches);
           VcGemmArgs g = base;
-          g.linv = dd_linv + (size_t)i * VC_TILE * VC_TILE;
+          g.linv = dd_linv + (size_t)k * VC_TILE * VC_TILE;
           g.jt = jt; g.K = VC_TILE;
           g.k0 = loc_tile_h(jt, nb, D->pc) * VC_TILE;
-          g.tiles = D->tiles_dev + s.d_trsm[i].off; g.ntiles = s.d_trsm[i].n;
+          g.tiles = D->tiles_dev + s.d_trsm[k].off; g.ntiles = s.d_trsm[k].n;
           vc_launch_trsm(g, g.ntiles, sp, &h->launches);
-          g.tiles = D->tiles_dev + s.d_inner[i].off; g.ntiles = s.d_inner[i].n;
+          g.tiles = D->tiles_dev + s.d_inner[k].off; g.ntiles = s.d_inner[k].n;
           vc_launch_syrk(g, h->cw.num_sms, h->cw.legacy_syrk, sp, &h->launches);
         }
         vc_launch_pack_tiles(base, D->tiles_dev + s.d_pack.off, s.d_pack.n,
@@ -388,54 +386,75 @@ int vc_dist_n2ll(vc_handle* h, const double* theta, int32_t mu_mode, const doubl
                                      ncclFloat64_, s.diag_owner, D->comm, sp));
       if (D->my_pc == s.pcp && s.rows.n > 0) {
         for (int jt = s.ob; jt < s.oe; ++jt) {
-          const int i = jt - s.ob;
+          const int k = jt - s.ob;
           VcGemmArgs g = base;
-          g.linv = dd_linv + (size_t)i * VC_TILE * VC_TILE;
+          g.linv = dd_linv + (size_t)k * VC_TILE * VC_TILE;
           g.jt = jt; g.K = VC_TILE;
           g.k0 = loc_tile_h(jt, nb, D->pc) * VC_TILE;
           g.tiles = D->tiles_dev + s.rows.off; g.ntiles = s.rows.n;
           vc_launch_trsm(g, g.ntiles, sp, &h->launches);
-          g.tiles = D->tiles_dev + s.inner[i].off; g.ntiles = s.inner[i].n;
+          g.tiles = D->tiles_dev + s.inner[k].off; g.ntiles = s.inner[k].n;
           g.src_b.pnl = D->dd; g.src_b.ld = VC_TILE; g.src_b.tile_stride = (int64_t)VC_TILE * Kb;
-          g.src_b.tile0 = s.ob; g.src_b.col0 = i * VC_TILE;
+          g.src_b.tile0 = s.ob; g.src_b.col0 = k * VC_TILE;
           vc_launch_syrk(g, h->cw.num_sms, h->cw.legacy_syrk, sp, &h->launches);
         }
         vc_launch_pack_tiles(base, D->tiles_dev + s.rows.off, s.rows.n,
                              loc_tile_h(s.ob, nb, D->pc) * VC_TILE, Kb, pnl, s.oe, sp, &h->launches);
       }
-      if (s.oe >= nt) continue;
-      if (D->world > 1) {
+      if (s.oe < nt && D->world > 1) {
         VC_NCCL_TRY(g_nccl.GroupStart());
         for (const BcastOp& op : s.bcasts)
           VC_NCCL_TRY(g_nccl.Broadcast(pnl + op.off, pnl + op.off, (size_t)op.count, ncclFloat64_, op.root,
                                        D->comm, sp));
         VC_NCCL_TRY(g_nccl.GroupEnd());
       }
-      // ---------------- trailing update (stream sm) ----------------
-      if (la) {
-        VC_CUDA_TRY(cudaEventRecord(h->cw.ev_panel, sp));
-        VC_CUDA_TRY(cudaStreamWaitEvent(sm, h->cw.ev_panel, 0));
-      }
+    };
+    // Lookahead, software-pipelined as in the single-GPU driver:
+    //   sm:  col(s) | rest A(s) on num_sms - R CTAs ...................... | rest B(s) on every SM | col(s+1)
+    //   sp:          panel phase (s+1): factor, NCCL broadcasts, solves ---^
+    // All NCCL calls are on sp, in the same order on every rank; the panel buffers are double-buffered.
+    const size_t nsteps = D->steps.size();
+    panel_phase(0);
+    if (la) VC_CUDA_TRY(cudaEventRecord(h->cw.ev_panel, sp));
+    for (size_t i = 0; i < nsteps; ++i) {
+      const DistStep& s = D->steps[i];
+      if (s.oe >= nt) break;
+      const int Kb = (s.oe - s.ob) * VC_TILE;
+      if (la) VC_CUDA_TRY(cudaStreamWaitEvent(sm, h->cw.ev_panel, 0));
       VcGemmArgs g = base;
       g.K = Kb;
-      g.src_a.pnl = pnl; g.src_a.ld = VC_TILE; g.src_a.tile_stride = (int64_t)VC_TILE * Kb;
+      g.src_a.pnl = D->pnl[i & 1]; g.src_a.ld = VC_TILE; g.src_a.tile_stride = (int64_t)VC_TILE * Kb;
       g.src_a.tile0 = s.oe; g.src_a.col0 = 0;
       g.src_b = g.src_a;
       g.tiles = D->tiles_dev + s.trailing_col.off; g.ntiles = s.trailing_col.n;
       vc_launch_syrk(g, h->cw.num_sms, h->cw.legacy_syrk, sm, &h->launches);
       if (la) {
-        // the next panel phase may start once its columns are up to date; it also must not
-        // overwrite the panel buffer the update two steps back was reading (ordered before on sm)
         VC_CUDA_TRY(cudaEventRecord(h->cw.ev_col, sm));
         VC_CUDA_TRY(cudaStreamWaitEvent(sp, h->cw.ev_col, 0));
       }
-      g.tiles = D->tiles_dev + s.trailing_rest.off; g.ntiles = s.trailing_rest.n;
+      const int rest = s.trailing_rest.n;
+      int nA = rest, reserve = 0;
+      if (la && !h->cw.legacy_syrk && i + 1 < nsteps) {
+        const DistStep& nx = D->steps[i + 1];
+        const bool in_col = (D->my_pc == nx.pcp);
+        // ranks of the next panel's process column run its solves beside the update; the others
+        // only need room for NCCL's kernels
+        reserve = in_col ? std::max(8, vc_pick_reserved_sms(h->cw.num_sms, std::max(nx.rows.n, 1), nb, rest, &nA)) : 6;
+        if (!in_col) nA = rest;
+      }
+      g.tiles = D->tiles_dev + s.trailing_rest.off; g.ntiles = nA;
       vc_launch_syrk(g, h->cw.num_sms - reserve, h->cw.legacy_syrk, sm, &h->launches);
+      if (i + 1 < nsteps) {
+        panel_phase(i + 1);
+        if (la) VC_CUDA_TRY(cudaEventRecord(h->cw.ev_panel, sp));
+      }
+      if (nA < rest) {
+        if (la) VC_CUDA_TRY(cudaStreamWaitEvent(sm, h->cw.ev_panel, 0));
+        g.tiles = D->tiles_dev + s.trailing_rest.off + nA; g.ntiles = rest - nA;
+        vc_launch_syrk(g, h->cw.num_sms, h->cw.legacy_syrk, sm, &h->launches);
+      }
     }
-    if (la) {
-      VC_CUDA_TRY(cudaEventRecord(h->cw.ev_panel, sp));
-      VC_CUDA_TRY(cudaStreamWaitEvent(sm, h->cw.ev_panel, 0));
-    }
+    if (la) VC_CUDA_TRY(cudaStreamWaitEvent(sm, h->cw.ev_panel, 0));
     VC_CUDA_TRY(cudaEventRecord(h->ev[2], st));
 
     // ---- finalize: local partials, three small all-reduces ----
