@@ -33,6 +33,14 @@ sys.path.insert(0, ROOT)
 # is ONE JSON line on stdout, so keep NCCL to warnings unless the caller asked for more
 if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
     os.environ["NCCL_DEBUG"] = "WARN"
+# ... and route everything any library writes to fd 1 to stderr; the JSON line goes to the real stdout
+_REAL_STDOUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(line: dict):
+    _REAL_STDOUT.write(json.dumps(line) + "\n")
+    _REAL_STDOUT.flush()
 
 WORKLOADS = {
     # name: (n, p=q, cov, taper, seed offset, description)
@@ -188,7 +196,7 @@ def run_reference(args):
             "cpu_baseline": arm,
             "e2e": {"value": arm["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "wall_s": wall}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -333,7 +341,7 @@ def run_ours(args):
     }
     if world == 1 and not args.no_cpu:
         line["cpu_baseline"] = cpu_arm(n, p, cov, seed_off, args.cpu_sample_n, 1)
-    print(json.dumps(line), flush=True)
+    emit(line)
     obj.close()
     if dist is not None:
         dist.destroy_process_group()
@@ -404,7 +412,7 @@ def run_dist(args):
                              "frac": n ** 3 / 3.0 / chol_s / 1e12 / (37.0 * world), "traffic": None,
                              "peak_source": "N x 37.0 TFLOP/s fp64 DMMA probe (vc_probe_dmma_peak)"},
                 "phases_ms": {k: v / K for k, v in phase.items()}, "n2ll_sample": vals[:2]}
-        print(json.dumps(line), flush=True)
+        emit(line)
     obj.close()
     dist.destroy_process_group()
 

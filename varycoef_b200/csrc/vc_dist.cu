@@ -433,25 +433,22 @@ int vc_dist_n2ll(vc_handle* h, const double* theta, int32_t mu_mode, const doubl
         VC_CUDA_TRY(cudaStreamWaitEvent(sp, h->cw.ev_col, 0));
       }
       const int rest = s.trailing_rest.n;
-      int nA = rest, reserve = 0;
+      // A persistent update kernel never yields an SM, so the rest update leaves R SMs to the panel
+      // stream.  Ranks of the NEXT panel's process column have real work there (TRSM + inner updates
+      // of their rows): R balances that work against the update (same cost model as the single-GPU
+      // driver).  The other ranks only need room for NCCL's kernels.
+      int reserve = 0, unused = 0;
       if (la && !h->cw.legacy_syrk && i + 1 < nsteps) {
         const DistStep& nx = D->steps[i + 1];
-        const bool in_col = (D->my_pc == nx.pcp);
-        // ranks of the next panel's process column run its solves beside the update; the others
-        // only need room for NCCL's kernels
-        reserve = in_col ? std::max(8, vc_pick_reserved_sms(h->cw.num_sms, std::max(nx.rows.n, 1), nb, rest, &nA)) : 6;
-        if (!in_col) nA = rest;
+        reserve = (D->my_pc == nx.pcp)
+                      ? std::max(8, vc_pick_reserved_sms(h->cw.num_sms, std::max(nx.rows.n, 1), nb, rest, &unused))
+                      : 6;
       }
-      g.tiles = D->tiles_dev + s.trailing_rest.off; g.ntiles = nA;
+      g.tiles = D->tiles_dev + s.trailing_rest.off; g.ntiles = rest;
       vc_launch_syrk(g, h->cw.num_sms - reserve, h->cw.legacy_syrk, sm, &h->launches);
       if (i + 1 < nsteps) {
         panel_phase(i + 1);
         if (la) VC_CUDA_TRY(cudaEventRecord(h->cw.ev_panel, sp));
-      }
-      if (nA < rest) {
-        if (la) VC_CUDA_TRY(cudaStreamWaitEvent(sm, h->cw.ev_panel, 0));
-        g.tiles = D->tiles_dev + s.trailing_rest.off + nA; g.ntiles = rest - nA;
-        vc_launch_syrk(g, h->cw.num_sms, h->cw.legacy_syrk, sm, &h->launches);
       }
     }
     if (la) VC_CUDA_TRY(cudaStreamWaitEvent(sm, h->cw.ev_panel, 0));

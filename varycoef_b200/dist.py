@@ -15,12 +15,14 @@ from .objective import SVCObjective
 
 
 def process_grid(world: int):
-    """pr x pc with pr <= pc, as square as possible: 1->1x1, 2->1x2, 4->2x2, 8->2x4."""
-    pr = 1
+    """pr x pc with pr >= pc, as square as possible: 1->1x1, 2->2x1, 4->2x2, 8->4x2.  More process
+    ROWS than columns: the rows of a panel (its TRSM / inner-update work, which overlaps the
+    trailing update on a handful of SMs only) are split over pr ranks."""
+    pc = 1
     for c in range(1, int(world ** 0.5) + 1):
         if world % c == 0:
-            pr = c
-    return pr, world // pr
+            pc = c
+    return world // pc, pc
 
 
 def nccl_unique_id() -> bytes:
