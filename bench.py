@@ -370,7 +370,7 @@ def run_dist(args):
     locs, X, y, L = make_inputs(n, p, seed_off)
     thetas = theta_stencil(n, p, q, L, y)
     K, Wm = args.steps, args.warmup
-    obj = distributed_objective(y, X, locs, cov_name=cov, profileLik=True, device=local)
+    obj = distributed_objective(y, X, locs, cov_name=cov, profileLik=True, device=local, nb_outer=args.nb)
     for s in range(Wm):
         obj.n2LL(thetas[s % len(thetas)])
     sampler = ClockSampler(local)
@@ -397,11 +397,13 @@ def run_dist(args):
         elapsed, launches = float(tmax[0]), int(t[1].item())
     if rank == 0:
         pr, pc = process_grid(world)
+        if os.environ.get("VC_GRID"):
+            pr, pc = (int(v) for v in os.environ["VC_GRID"].split("x"))
         chol_s = phase["chol_ms"] / K * 1e-3
         line = {"metric": "-2logL evals/sec (fp64), one evaluation sharded 2D block-cyclic", "value": K / elapsed,
                 "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": elapsed / K * 1e3,
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": desc, "n": n, "p": p, "q": q, "cov": cov, "grid": "%dx%d" % (pr, pc),
+                "config": {"workload": desc, "n": n, "p": p, "q": q, "cov": cov, "grid": "%dx%d" % (pr, pc), "nb_outer": args.nb or "auto",
                            "parallelism": "2D block-cyclic Sigma_y, NCCL panel broadcasts, lookahead",
                            "l2": "inputs larger than L2"},
                 "clocks": clocks, "gpu_launches": launches,
@@ -427,6 +429,7 @@ def main():
     ap.add_argument("--n", "--problem-n", dest="n", type=int, default=0, help="override n (debug; use --problem-n under torchrun)")
     ap.add_argument("--cpu-sample-n", type=int, default=6000)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--nb", type=int, default=0, help="outer Cholesky block (0 = auto)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

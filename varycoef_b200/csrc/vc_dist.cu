@@ -23,6 +23,7 @@
 #include <math.h>
 #include <string.h>
 #include <algorithm>
+#include <stdlib.h>
 
 // ---- host-only block-cyclic maps (exported; unit-tested on the CPU) --------------------------
 extern "C" int vc_bc_owner(int32_t bi, int32_t bj, int32_t pr, int32_t pc) {
@@ -434,15 +435,14 @@ int vc_dist_n2ll(vc_handle* h, const double* theta, int32_t mu_mode, const doubl
       }
       const int rest = s.trailing_rest.n;
       // A persistent update kernel never yields an SM, so the rest update leaves R SMs to the panel
-      // stream.  Ranks of the NEXT panel's process column have real work there (TRSM + inner updates
-      // of their rows): R balances that work against the update (same cost model as the single-GPU
-      // driver).  The other ranks only need room for NCCL's kernels.
-      int reserve = 0, unused = 0;
+      // stream (potrf chain, the column ranks' TRSM + inner updates, NCCL's kernels).  Measured at
+      // n = 150 000 on 8 GPUs (4x2): R = 8 -> 4.70 s, R = 16 -> 4.55 s per evaluation; the per-rank
+      // cost model of the single-GPU driver did worse (5.7 s): every rank is slowed to the pace of
+      // the slowest one at each panel broadcast, so a uniform R wins.  VC_DIST_RESERVE overrides.
+      int reserve = 0;
       if (la && !h->cw.legacy_syrk && i + 1 < nsteps) {
-        const DistStep& nx = D->steps[i + 1];
-        reserve = (D->my_pc == nx.pcp)
-                      ? std::max(8, vc_pick_reserved_sms(h->cw.num_sms, std::max(nx.rows.n, 1), nb, rest, &unused))
-                      : 6;
+        static const int fixed = getenv("VC_DIST_RESERVE") ? atoi(getenv("VC_DIST_RESERVE")) : 16;
+        reserve = std::min(fixed, h->cw.num_sms / 2);
       }
       g.tiles = D->tiles_dev + s.trailing_rest.off; g.ntiles = rest;
       vc_launch_syrk(g, h->cw.num_sms - reserve, h->cw.legacy_syrk, sm, &h->launches);

@@ -39,6 +39,9 @@ def distributed_objective(y, X, locs, W=None, grid=None, device=None, **kw) -> S
     if not dist.is_initialized():
         raise RuntimeError("torch.distributed must be initialised (torchrun) before distributed_objective")
     rank, world = dist.get_rank(), dist.get_world_size()
+    import os
+    if grid is None and os.environ.get("VC_GRID"):
+        grid = tuple(int(v) for v in os.environ["VC_GRID"].split("x"))
     pr, pc = grid if grid is not None else process_grid(world)
     if pr * pc != world:
         raise ValueError("grid %dx%d does not match world size %d" % (pr, pc, world))
