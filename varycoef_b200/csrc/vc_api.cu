@@ -5,6 +5,7 @@
 #include <string.h>
 #include <limits.h>
 #include <new>
+#include <algorithm>
 
 static thread_local std::string g_create_error;
 
@@ -58,6 +59,20 @@ void vc_free_handle(vc_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   if (h->dist) vc_dist_destroy(h);
+  for (VcLane* L : h->lanes) {
+    cudaFree(L->M.a); cudaFree(L->M.b); vc_chol_free_plans(L->cw);
+    cudaFree(L->cw.linv); cudaFree(L->cw.logdet_part); cudaFree(L->cw.info);
+    cudaFree(L->fw.gram_part); cudaFree(L->fw.quad_part); cudaFree(L->gram_dev);
+    if (L->cw.ev_panel) cudaEventDestroy(L->cw.ev_panel);
+    if (L->cw.ev_update) cudaEventDestroy(L->cw.ev_update);
+    if (L->cw.ev_col) cudaEventDestroy(L->cw.ev_col);
+    if (L->ev_done) cudaEventDestroy(L->ev_done);
+    if (L->st_main) cudaStreamDestroy(L->st_main);
+    if (L->st_panel) cudaStreamDestroy(L->st_panel);
+    delete L;
+  }
+  h->lanes.clear();
+  if (h->ev_inputs) cudaEventDestroy(h->ev_inputs);
   cudaFree(h->M.a); cudaFree(h->M.b); vc_chol_free_plans(h->cw); cudaFree(h->locs); cudaFree(h->x); cudaFree(h->w); cudaFree(h->y);
   cudaFree(h->mu_in); cudaFree(h->results); cudaFree(h->gram_dev);
   if (h->results_host) cudaFreeHost(h->results_host);
@@ -189,6 +204,7 @@ extern "C" int vc_set_data(vc_handle* h, const double* locs, const double* X, co
     if (y) upload_padded(h->y, y, h->n, h->n_pad, 1, h->st_main);
     h->factor_valid = false;
     h->factor_theta.clear();
+    for (VcLane* L : h->lanes) L->factor_theta.clear();
   } catch (const VcError& e) {
     return vc_fail(h, e.code, e.msg);
   }
@@ -215,30 +231,72 @@ int vc_make_theta(const vc_handle* h, const double* theta, VcTheta* t) {
   return VC_OK;
 }
 
-// enqueue one evaluation on the handle's streams; result record `slot`.  When theta equals the
-// theta of the factor already resident (optim's probes of the mean parameters in the non-profile
-// objective, vc_post after a fit), only the O(n p) finalize runs.
-static void enqueue_eval(vc_handle* h, const VcTheta& th, const double* theta, int mu_mode, int slot,
-                         bool timed) {
-  cudaStream_t st = h->st_main;
+// how many evaluation lanes a batch may use: one evaluation fills the GPU from n ~ 20k on
+static int lane_cap(const vc_handle* h) {
+  if (h->dist) return 1;
+  if (h->n_pad <= 12288) return 4;
+  if (h->n_pad <= 24576) return 2;
+  return 1;
+}
+
+static VcLane* make_lane(vc_handle* h) {
+  VcLane* L = new VcLane();
+  h->lanes.push_back(L);
+  const int64_t np = h->n_pad;
+  int lo = 0, hi = 0;
+  VC_CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+  VC_CUDA_TRY(cudaStreamCreateWithPriority(&L->st_main, cudaStreamNonBlocking, lo));
+  VC_CUDA_TRY(cudaStreamCreateWithPriority(&L->st_panel, cudaStreamNonBlocking, hi));
+  VC_CUDA_TRY(cudaEventCreateWithFlags(&L->cw.ev_panel, cudaEventDisableTiming));
+  VC_CUDA_TRY(cudaEventCreateWithFlags(&L->cw.ev_update, cudaEventDisableTiming));
+  VC_CUDA_TRY(cudaEventCreateWithFlags(&L->cw.ev_col, cudaEventDisableTiming));
+  VC_CUDA_TRY(cudaEventCreateWithFlags(&L->ev_done, cudaEventDisableTiming));
+  L->M = h->M;
+  L->M.a = nullptr; L->M.b = nullptr;
+  L->M.nbt = 1; L->M.ldb = VC_BORDER_ROWS;
+  VC_CUDA_TRY(cudaMalloc(&L->M.a, (size_t)L->M.lda * np * sizeof(double)));
+  VC_CUDA_TRY(cudaMalloc(&L->M.b, (size_t)L->M.ldb * np * sizeof(double)));
+  L->cw.nb_tiles = h->cw.nb_tiles; L->cw.lookahead = h->cw.lookahead;
+  L->cw.legacy_syrk = h->cw.legacy_syrk; L->cw.legacy_potrf = h->cw.legacy_potrf; L->cw.num_sms = h->cw.num_sms;
+  L->cw.st_main = L->st_main; L->cw.st_panel = L->st_panel;
+  VC_CUDA_TRY(cudaMalloc(&L->cw.linv, (size_t)L->M.nt * VC_TILE * VC_TILE * sizeof(double)));
+  VC_CUDA_TRY(cudaMalloc(&L->cw.logdet_part, (size_t)L->M.nt * sizeof(double)));
+  VC_CUDA_TRY(cudaMalloc(&L->cw.info, sizeof(int)));
+  const int m = h->p + 1;
+  L->fw.blocks = h->fw.blocks;
+  VC_CUDA_TRY(cudaMalloc(&L->fw.gram_part, (size_t)L->fw.blocks * m * (m + 1) * sizeof(double)));
+  VC_CUDA_TRY(cudaMalloc(&L->fw.quad_part, (size_t)L->fw.blocks * 2 * sizeof(double)));
+  VC_CUDA_TRY(cudaMalloc(&L->gram_dev, (size_t)m * m * sizeof(double)));
+  return L;
+}
+
+// enqueue one evaluation on a lane (lane < 0: the handle's own matrix and streams); result record
+// `slot`.  When theta equals the theta of the factor already resident in that lane (optim's probes of
+// the mean parameters in the non-profile objective, vc_post after a fit), only the O(n p) finalize runs.
+static void enqueue_eval(vc_handle* h, int lane, const VcTheta& th, const double* theta, int mu_mode,
+                         int slot, bool timed) {
+  VcLane* L = lane >= 0 ? h->lanes[lane] : nullptr;
+  VcMatrix& M = L ? L->M : h->M;
+  VcCholWork& cw = L ? L->cw : h->cw;
+  VcFinalWork& fw = L ? L->fw : h->fw;
+  std::vector<double>& ft = L ? L->factor_theta : h->factor_theta;
+  cudaStream_t st = L ? L->st_main : h->st_main;
   const size_t nth = (size_t)2 * h->q + 1;
-  const bool cached = h->factor_theta.size() == nth &&
-                      memcmp(h->factor_theta.data(), theta, nth * sizeof(double)) == 0;
+  const bool cached = ft.size() == nth && memcmp(ft.data(), theta, nth * sizeof(double)) == 0;
   if (timed) VC_CUDA_TRY(cudaEventRecord(h->ev[0], st));
   if (!cached) {
-    vc_launch_build(h->M, th, h->d, h->locs, h->w, st, &h->launches);
-    vc_launch_border(h->M, h->p, h->x, h->y, st, &h->launches);
+    vc_launch_build(M, th, h->d, h->locs, h->w, st, &h->launches);
+    vc_launch_border(M, h->p, h->x, h->y, st, &h->launches);
   }
   if (timed) VC_CUDA_TRY(cudaEventRecord(h->ev[1], st));
   if (!cached) {
-    h->M.nbt = 1;
-    vc_chol_factor(h->M, h->cw, &h->launches);
-    h->factor_theta.assign(theta, theta + nth);
+    M.nbt = 1;
+    vc_chol_factor(M, cw, &h->launches);
+    ft.assign(theta, theta + nth);
   }
   if (timed) VC_CUDA_TRY(cudaEventRecord(h->ev[2], st));
-  vc_launch_finalize(h->M, h->p, mu_mode, h->mu_in + (size_t)slot * 128, h->cw.logdet_part,
-                     h->cw.info, h->fw, h->results + (size_t)slot * VC_RES_STRIDE, st, &h->launches,
-                     h->gram_dev);
+  vc_launch_finalize(M, h->p, mu_mode, h->mu_in + (size_t)slot * 128, cw.logdet_part, cw.info, fw,
+                     h->results + (size_t)slot * VC_RES_STRIDE, st, &h->launches, L ? L->gram_dev : h->gram_dev);
   if (timed) VC_CUDA_TRY(cudaEventRecord(h->ev[3], st));
 }
 
@@ -269,13 +327,27 @@ extern "C" int vc_n2ll_batch(vc_handle* h, int32_t m, const double* thetas, int3
     if (mu_mode == VC_MU_FIXED)
       VC_CUDA_TRY(cudaMemcpy2DAsync(h->mu_in, 128 * sizeof(double), mus_in, h->p * sizeof(double),
                                     h->p * sizeof(double), m, cudaMemcpyHostToDevice, h->st_main));
+    // lanes: evaluation e runs on lane (m - 1 - e) % nl, so the LAST one lands on the handle's own
+    // matrix (vc_get_chol / vc_get_whitened / vc_post refer to it)
+    const int nl = std::min(m, lane_cap(h));
+    while ((int)h->lanes.size() < nl - 1) make_lane(h);
+    if (nl > 1) {
+      if (!h->ev_inputs) VC_CUDA_TRY(cudaEventCreateWithFlags(&h->ev_inputs, cudaEventDisableTiming));
+      VC_CUDA_TRY(cudaEventRecord(h->ev_inputs, h->st_main));   // inputs / mu staged on st_main
+      for (int l = 0; l < nl - 1; ++l) VC_CUDA_TRY(cudaStreamWaitEvent(h->lanes[l]->st_main, h->ev_inputs, 0));
+    }
     for (int e = 0; e < m; ++e) {
       VcTheta th;
       if (vc_make_theta(h, thetas + (size_t)e * nth, &th) != VC_OK) {
         status[e] = VC_ERR_INVALID;
         continue;
       }
-      enqueue_eval(h, th, thetas + (size_t)e * nth, mu_mode, e, e == m - 1);
+      const int lane = (m - 1 - e) % nl;              // 0 = the handle itself
+      enqueue_eval(h, lane - 1, th, thetas + (size_t)e * nth, mu_mode, e, e == m - 1);
+    }
+    for (int l = 0; l < nl - 1; ++l) {
+      VC_CUDA_TRY(cudaEventRecord(h->lanes[l]->ev_done, h->lanes[l]->st_main));
+      VC_CUDA_TRY(cudaStreamWaitEvent(h->st_main, h->lanes[l]->ev_done, 0));
     }
     VC_CUDA_TRY(cudaMemcpyAsync(h->results_host, h->results, (size_t)m * VC_RES_STRIDE * sizeof(double),
                                 cudaMemcpyDeviceToHost, h->st_main));
@@ -312,6 +384,7 @@ extern "C" int vc_n2ll_batch(vc_handle* h, int32_t m, const double* thetas, int3
     }
   } catch (const VcError& e) {
     h->factor_theta.clear();
+    for (VcLane* L : h->lanes) L->factor_theta.clear();
     h->factor_valid = false;
     return vc_fail(h, e.code, e.msg);
   }

@@ -905,7 +905,13 @@ void vc_chol_factor(const VcMatrix& M, VcCholWork& w, int64_t* launches, int mod
     VC_CUDA_TRY(cudaStreamWaitEvent(sp, w.ev_col, 0));
     const int rest_tiles = pl.calls[c_rest].ntiles;
     int nA = rest_tiles;
-    const int reserve = w.legacy_syrk ? 0 : vc_pick_reserved_sms(w.num_sms, nt + nbt - oe, nb, rest_tiles, &nA);
+    int reserve = w.legacy_syrk ? 0 : vc_pick_reserved_sms(w.num_sms, nt + nbt - oe, nb, rest_tiles, &nA);
+    {  // tuning overrides: VC_RESERVE_SMS = fixed R, VC_NO_SPLIT = run the whole rest update on num_sms - R
+      static const int fixed = getenv("VC_RESERVE_SMS") ? atoi(getenv("VC_RESERVE_SMS")) : -1;
+      static const bool nosplit = getenv("VC_NO_SPLIT") != nullptr;
+      if (fixed >= 0 && !w.legacy_syrk) reserve = fixed;
+      if (nosplit) nA = rest_tiles;
+    }
     launch_update(M, w, pl, c_rest, sm, launches, reserve, 0, nA);
     panel(oe);
     VC_CUDA_TRY(cudaEventRecord(w.ev_panel, sp));

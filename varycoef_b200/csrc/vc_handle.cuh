@@ -2,6 +2,19 @@
 #pragma once
 #include "vc_common.cuh"
 
+// An extra evaluation lane: its own matrix, factor workspace and streams.  vc_n2ll_batch spreads the
+// evaluations of a batch over the lanes when one evaluation cannot fill the GPU (n_pad <= 16384), the
+// single-GPU analogue of the reference's optimParallel fan-out (R-pkg/R/SVC_mle.R:164-200).
+struct VcLane {
+  VcMatrix M{};
+  VcCholWork cw{};
+  VcFinalWork fw{};
+  double* gram_dev = nullptr;
+  cudaStream_t st_main = nullptr, st_panel = nullptr;
+  cudaEvent_t ev_done = nullptr;
+  std::vector<double> factor_theta;
+};
+
 struct vc_handle {
   vc_config cfg;
   int64_t n = 0, n_pad = 0;
@@ -23,6 +36,8 @@ struct vc_handle {
   bool factor_valid = false;
   std::vector<double> factor_theta;  // theta of the factor resident in M (empty = none)
   double* gram_dev = nullptr;        // (p+1)^2 Gram of the whitened [X y] of the last evaluation
+  std::vector<VcLane*> lanes;        // extra lanes (lane 0 is the handle itself), created on demand
+  cudaEvent_t ev_inputs = nullptr;   // batch inputs (mu) staged on st_main
   int64_t launches = 0;
   std::string err;
   // distributed state lives in vc_dist.cu
