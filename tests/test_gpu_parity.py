@@ -552,3 +552,16 @@ def test_config_c5_n20000_tapered_dense_on_gpu():
     ref = n * np.log(2 * np.pi) + logdet + float((rz @ rz).item())
     assert abs(r["n2ll"] - ref) <= TOL_N2LL * abs(ref)
     assert _rel(r["mu"], mu) <= 1e-9
+
+
+def test_fallback_kernels_agree_with_default_path():
+    """VC_FLAG_LEGACY_POTRF (unblocked diagonal-tile kernel) and VC_FLAG_NO_LOOKAHEAD give the same
+    likelihood as the default kernels up to rounding."""
+    from varycoef_b200 import SVCObjective
+    locs, X, W, y = synth(2100, 3, 4242, 2)
+    theta = theta_for(3)
+    with SVCObjective(y, X, locs, profileLik=True) as obj:
+        v = obj.n2LL(theta)
+    for kw in ({"legacy_potrf": True}, {"lookahead": False}, {"legacy_potrf": True, "legacy_syrk": True, "lookahead": False}):
+        with SVCObjective(y, X, locs, profileLik=True, **kw) as o2:
+            assert abs(o2.n2LL(theta) - v) <= 1e-13 * abs(v), kw
