@@ -190,3 +190,23 @@ int main(){ double tab[64]; vc_fill_exp2_table(tab); double mx=0; srand(7);
         subprocess.check_call(["g++", "-O2", "-x", "c++", "-I", os.path.join(ROOT, "varycoef_b200", "csrc"), cpp, "-o", exe])
         mx, e0, e800 = subprocess.check_output([exe], text=True).split()
     assert float(mx) < 4.5e-16 and float(e0) == 1.0 and float(e800) == 0.0
+
+
+def test_graft_entry_build_and_reference_arm_json():
+    """build() compiles / loads the library without a GPU; `bench.py --impl reference` prints exactly one
+    JSON line on stdout with the contract's keys."""
+    import json
+    sys.path.insert(0, ROOT)
+    import __graft_entry__ as g
+    g.build()
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "1", "--cpu-sample-n", "600"], cwd=ROOT, capture_output=True, text=True,
+                         timeout=300)
+    assert out.returncode == 0, out.stderr[-500:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "evals/s" and d["higher_is_better"] is True
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["value"] > 0
+    assert d["metric"].startswith("-2logL evals/sec")
