@@ -7,4 +7,7 @@ R interface.  There is no CPU path.
 """
 from .objective import SVCObjective, n2LL, GLS_chol, pc_penalty, check_cov_lower  # noqa: F401
 
-__all__ = ["SVCObjective", "n2LL", "GLS_chol", "pc_penalty", "check_cov_lower"]
+from .svc_selection import SVC_selection, SVC_selection_control  # noqa: F401,E402
+
+__all__ = ["SVCObjective", "n2LL", "GLS_chol", "pc_penalty", "check_cov_lower", "SVC_selection",
+           "SVC_selection_control"]
