@@ -565,3 +565,25 @@ def test_fallback_kernels_agree_with_default_path():
     for kw in ({"legacy_potrf": True}, {"lookahead": False}, {"legacy_potrf": True, "legacy_syrk": True, "lookahead": False}):
         with SVCObjective(y, X, locs, profileLik=True, **kw) as o2:
             assert abs(o2.n2LL(theta) - v) <= 1e-13 * abs(v), kw
+
+
+@pytest.mark.parametrize("name", ["vignette_n100_exp", "synthetic_n260_mat32"])
+def test_gpu_within_1e12_of_40_digit_value(name):
+    """SURVEY 8(c) precision plan: -2logL, log-det, quadratic form and the GLS mean from the GPU sit within 1e-12
+    (relative) of the 40-digit evaluation of the same fp64 inputs (tests/golden/highprec_golden.json)."""
+    import json
+    import os
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, os.path.join(here, "golden"))
+    import make_highprec as hp
+    from varycoef_b200 import SVCObjective
+    g = json.load(open(os.path.join(here, "golden", "highprec_golden.json")))[name]
+    y, X, W, locs, theta, cov = hp.case_inputs(name)
+    with SVCObjective(y, X, locs, W, cov_name=cov, profileLik=True) as obj:
+        r = obj.n2LL(theta, parts=True)
+    for k in ("n2ll", "logdet", "quad"):
+        rel = abs(r[k] - float(g[k])) / abs(float(g[k]))
+        print("%s %s: gpu %.17g true %s rel %.2e" % (name, k, r[k], g[k], rel))
+        assert rel <= 1e-12, (k, r[k], g[k])
+    assert np.allclose(r["mu"], [float(v) for v in g["mu"]], rtol=1e-12, atol=0)
