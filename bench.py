@@ -53,6 +53,9 @@ WORKLOADS = {
 TRUE_VAR = [2.0, 1.0, 1.5, 1.0, 0.5]
 TRUE_SCALE = [3.0, 1.0, 2.0, 1.5, 2.5]
 TRUE_MEAN = [1.0, 2.0, 0.5, -1.0, 0.0]
+# DRAM bytes per evaluation from ncu (dram__bytes_read.sum + dram__bytes_write.sum), profiles/r01_traffic_n50k.md
+NCU_TRAFFIC_BYTES = {"c3": 6.163e11}           # potrf + trsm + syrk kernels of one C3 evaluation
+NCU_BUILD_TRAFFIC_BYTES = {"c3": 1.002e10}     # k_build_fast + k_border (algorithmic: 1.0e10 written)
 METRIC = "-2logL evals/sec (fp64) at n=50k q=3"
 UNIT = "evals/s"
 
@@ -311,15 +314,17 @@ def run_ours(args):
     roof = {"bound": "tensor", "kernel": "k_syrk_ws (persistent TMA-fed DMMA trailing SYRK) inside the bordered Cholesky",
             "achieved": chol_flops / chol_s / 1e12, "peak": peak_tf.value, "unit": "TFLOP/s",
             "frac": chol_flops / chol_s / 1e12 / peak_tf.value if peak_tf.value > 0 else None,
-            "traffic": None,
-            "traffic_note": "ncu --set full of one k_syrk_ws launch at n=20k (profiles/r01_syrk_ws_n20k.md): 3.9 GB DRAM "
-                            "for 1.9e11 flop -- 8 % of DRAM peak, DMMA pipe 95.7 % active: compute-bound",
+            "traffic": NCU_TRAFFIC_BYTES.get(args.workload) if n == WORKLOADS[args.workload][0] else None,
+            "traffic_note": "DRAM read + write bytes of all Cholesky kernels of ONE evaluation (per evaluation, like "
+                            "`achieved`), ncu dram__bytes_{read,write}.sum, profiles/r01_traffic_n50k.md: 616 GB in "
+                            "1.21 s = 8 % of DRAM peak -- the factorisation is DMMA-bound (pipe 95.7 % active in "
+                            "k_syrk_ws, profiles/r01_syrk_ws_n20k.md); the C trapezoid alone accounts for ~400 GB",
             "peak_source": "fp64 DMMA m8n8k4 register-resident probe measured live on this GPU (vc_probe_dmma_peak); "
                            "MEASURED_PEAKS.json has no fp64 entry",
             "algorithmic": "n^3/3 flops per evaluation / CUDA-event time of the whole factorisation (panels included)"}
     roof_build = {"bound": "hbm", "kernel": "k_build_fast (fused distance + covariance)", "achieved": build_bytes / build_s / 1e9,
                   "peak": hbm_peak, "unit": "GB/s", "frac": build_bytes / build_s / 1e9 / hbm_peak,
-                  "traffic": None, "peak_source": hbm_src,
+                  "traffic": NCU_BUILD_TRAFFIC_BYTES.get(args.workload) if n == WORKLOADS[args.workload][0] else None, "peak_source": hbm_src,
                   "algorithmic": "4 n (n+1) bytes written (lower triangle) / CUDA-event time of build + border"}
     h2d = 8 * n * (2 + p + q + 1) + 8 * (2 * q + 1)
     d2h = 8 * 132
