@@ -645,6 +645,436 @@ k_potrf128b(double* __restrict__ At, int64_t lda, int jt, double* __restrict__ l
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// k_potrf128c (default): latency-oriented version of k_potrf128b, same storage and same outputs.
+// The chain of 128 pivots bounds this kernel, so
+//  * the 16x16 diagonal block is factored AND inverted by one warp entirely in registers: lane i
+//    owns row i, pivots and column entries travel by shuffles, 1/sqrt by rsqrt.approx + Newton --
+//    no shared-memory round trip and no CTA barrier inside the 16 pivot steps (~135 cycles/pivot);
+//  * while warp 0 does that, warps 1..7 finish the previous rank-16 update and assemble the block
+//    row of the inverse that became computable (X_ij = -X_ii sum_k L_ik X_kj), so neither sits on
+//    the critical path; only the three 8x8 pairs of the next diagonal block are updated first;
+//  * tile load / store are 16-byte, the inverse is written through 4x8 patches (full 32-byte
+//    sectors in global memory, conflict-free in shared memory).
+// ---------------------------------------------------------------------------------------------
+constexpr int POTRFC_SMEM = ((TILE + 1) * PLD + TILE + 8 * PB * SS_LD) * (int)sizeof(double);
+#ifdef VC_POTRF_CLOCKS   // tools/potrf_probe.cu: cycle stamps at the phase boundaries
+__device__ long long g_potrf_clk[64];
+#define POTRF_STAMP(k) do { if (threadIdx.x == 0) g_potrf_clk[k] = clock64(); __syncwarp(); } while (0)
+#else
+#define POTRF_STAMP(k) do { } while (0)
+#endif
+
+// 1 / sqrt(s) to ~1 ulp (s > 0); NaN / inf for s <= 0 so that a bad pivot poisons what follows
+__device__ __forceinline__ double rsqrt_newton(double s) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(s));
+  const double hs = 0.5 * s;
+  y = y * fma(-hs * y, y, 1.5);
+  y = y * fma(-hs * y, y, 1.5);
+  return y;
+}
+
+// rank-16 update of the 8x8 pair t of the trailing lower triangle behind block column k0 / 16
+__device__ __forceinline__ void potrf_update_pair(double* M, int k0, int t, int g, int tig) {
+  int sa = (int)((sqrtf(8.0f * t + 1.0f) - 1.0f) * 0.5f);
+  while ((sa + 1) * (sa + 2) / 2 <= t) ++sa;
+  while (sa * (sa + 1) / 2 > t) --sa;
+  const int sb = t - sa * (sa + 1) / 2;
+  const int rowA = k0 + PB + 8 * sa, rowB = k0 + PB + 8 * sb;
+  double c0 = M[(rowB + 2 * tig) * PLD + rowA + g];
+  double c1 = M[(rowB + 2 * tig + 1) * PLD + rowA + g];
+#pragma unroll
+  for (int k4 = 0; k4 < 4; ++k4) {
+    const int k = k0 + 4 * k4 + tig;
+    dmma884(c0, c1, -M[k * PLD + rowA + g], M[k * PLD + rowB + g]);
+  }
+  if (sa != sb || g >= 2 * tig) M[(rowB + 2 * tig) * PLD + rowA + g] = c0;
+  if (sa != sb || g >= 2 * tig + 1) M[(rowB + 2 * tig + 1) * PLD + rowA + g] = c1;
+}
+
+// one 16x16 block of the inverse: X_ij = -X_ii * sum_{k=j}^{i-1} L_ik X_kj (one warp, DMMA)
+__device__ __forceinline__ void potrf_xrow_item(double* M, double* ss, int bi, int bj, int g, int tig) {
+  double s[2][2][2];
+#pragma unroll
+  for (int mm = 0; mm < 2; ++mm)
+#pragma unroll
+    for (int nn = 0; nn < 2; ++nn) s[mm][nn][0] = s[mm][nn][1] = 0.0;
+  for (int kbk = bj; kbk < bi; ++kbk) {
+#pragma unroll
+    for (int k4 = 0; k4 < 4; ++k4) {
+      const int kk = 4 * k4 + tig;
+      double af[2], bf[2];
+#pragma unroll
+      for (int mm = 0; mm < 2; ++mm) af[mm] = M[(PB * kbk + kk) * PLD + PB * bi + 8 * mm + g];
+#pragma unroll
+      for (int nn = 0; nn < 2; ++nn) {
+        const int n = 8 * nn + g;
+        bf[nn] = (kbk > bj || kk >= n) ? M[(PB * kbk + kk + 1) * PLD + PB * bj + n] : 0.0;
+      }
+#pragma unroll
+      for (int mm = 0; mm < 2; ++mm)
+#pragma unroll
+        for (int nn = 0; nn < 2; ++nn) dmma884(s[mm][nn][0], s[mm][nn][1], af[mm], bf[nn]);
+    }
+  }
+  __syncwarp();
+#pragma unroll
+  for (int mm = 0; mm < 2; ++mm)
+#pragma unroll
+    for (int nn = 0; nn < 2; ++nn) {
+      ss[(8 * nn + 2 * tig) * SS_LD + 8 * mm + g] = s[mm][nn][0];
+      ss[(8 * nn + 2 * tig + 1) * SS_LD + 8 * mm + g] = s[mm][nn][1];
+    }
+  __syncwarp();
+  double xo[2][2][2];
+#pragma unroll
+  for (int mm = 0; mm < 2; ++mm)
+#pragma unroll
+    for (int nn = 0; nn < 2; ++nn) xo[mm][nn][0] = xo[mm][nn][1] = 0.0;
+#pragma unroll
+  for (int k4 = 0; k4 < 4; ++k4) {
+    const int kk = 4 * k4 + tig;
+    double af[2], bf[2];
+#pragma unroll
+    for (int mm = 0; mm < 2; ++mm) {
+      const int r = 8 * mm + g;
+      af[mm] = (kk <= r) ? -M[(PB * bi + r + 1) * PLD + PB * bi + kk] : 0.0;
+    }
+#pragma unroll
+    for (int nn = 0; nn < 2; ++nn) bf[nn] = ss[(8 * nn + g) * SS_LD + kk];
+#pragma unroll
+    for (int mm = 0; mm < 2; ++mm)
+#pragma unroll
+      for (int nn = 0; nn < 2; ++nn) dmma884(xo[mm][nn][0], xo[mm][nn][1], af[mm], bf[nn]);
+  }
+#pragma unroll
+  for (int mm = 0; mm < 2; ++mm)
+#pragma unroll
+    for (int nn = 0; nn < 2; ++nn) {
+      double* dst = M + (PB * bi + 8 * mm + g + 1) * PLD + PB * bj + 8 * nn + 2 * tig;
+      dst[0] = xo[mm][nn][0];
+      dst[1] = xo[mm][nn][1];
+    }
+}
+
+// 16x16 diagonal block at (k0, k0): factor (FACTOR) and invert, one warp.  Lane i (and its mirror
+// i + 16) owns row i in registers.  The dependent chain per pivot is
+//   1/sqrt (MUFU + 3rd-order correction) -> scale own column entry -> own diagonal -> shuffle,
+// everything else (the rank-1 update of the other columns) reads the scaled column back from
+// shared memory (its final location in M) as broadcast 16-byte loads and fills the issue slots
+// the chain leaves free.  Template recursion keeps every register-array index a compile-time
+// constant (a partially unrolled loop would push the arrays to local memory).
+struct DiagRegs {
+  double a[PB], invd[PB], x[PB];
+  double dg, mydiag;
+  int bad;
+};
+// 1 / sqrt(s): rsqrt.approx (~2^-22) + one third-order step r (1 + e/2 + 3 e^2 / 8), e = 1 - s r^2
+__device__ __forceinline__ double rsqrt3(double s) {
+  double y0;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(s));
+  const double t = s * y0;
+  const double e = fma(-t, y0, 1.0);
+  const double c = fma(0.375, e, 0.5);
+  return fma(y0 * e, c, y0);
+}
+// Column values fetched in step J are consumed in step J + 1 (software pipelining by one step): the
+// loads have a whole pivot chain of time to land, so the single warp never stalls on them.
+struct DiagCol { double v[PB]; };
+template <int J, int K>
+__device__ __forceinline__ void potrf_diag_fetch(DiagCol& C, const double* Mb) {   // C.v[K] = L(K, J), K >= J + 2
+  if constexpr (K < PB) {
+    if constexpr (K % 2 == 0 && K + 1 < PB) {
+      const double2 v = *reinterpret_cast<const double2*>(Mb + J * PLD + K);
+      C.v[K] = v.x;
+      C.v[K + 1] = v.y;
+      potrf_diag_fetch<J, K + 2>(C, Mb);
+    } else {
+      C.v[K] = Mb[J * PLD + K];
+      potrf_diag_fetch<J, K + 1>(C, Mb);
+    }
+  }
+}
+template <int K>
+__device__ __forceinline__ void potrf_diag_apply(DiagRegs& R, const DiagCol& C, double lprev) {
+  if constexpr (K < PB) {
+    R.a[K] = fma(-lprev, C.v[K], R.a[K]);
+    potrf_diag_apply<K + 1>(R, C, lprev);
+  }
+}
+// Pivot J from its value p: r = 1 / sqrt(p) for everyone, sqrt(p) kept by lane J
+__device__ __forceinline__ double potrf_diag_pivot(DiagRegs& R, int J, int i, double p) {
+  if (!(p > 0.0)) R.bad = min(R.bad, J);
+  const double r = rsqrt3(p);
+  double sq = p * r;
+  sq = fma(fma(-sq, sq, p), 0.5 * r, sq);
+  R.mydiag = (i == J) ? sq : R.mydiag;
+  return r;
+}
+// One pivot step.  On entry r = 1 / L(J, J); u = A'(J+1, J) and q = A'(J+1, J+1) are the not yet
+// scaled column-J entry and the diagonal of row J+1 (updated through column J-1), broadcast one
+// step ahead, so that EVERY lane can form L(J+1, J) = u r and the next pivot q - L(J+1, J)^2 itself:
+// the dependent chain from one pivot to the next is  mul -> fma -> rsqrt  with no shuffle in it.
+// Cp = column J-1 below row J (fetched in the previous step), lprev = L(i, J-1).
+// R.a[J] arrives masked (0 for lanes i <= J).
+template <int J>
+__device__ __forceinline__ void potrf_diag_step(DiagRegs& R, double* Mb, int i, bool st, double r, double u,
+                                                double q, const DiagCol& Cp, double lprev) {
+  if constexpr (J < PB) {
+    R.invd[J] = r;
+    const double lij = R.a[J] * r;
+    R.dg = fma(-lij, lij, R.dg);
+    double rn = 0.0, un = 0.0, qn = 0.0;
+    if constexpr (J + 1 < PB) {
+      const double l1 = u * r;                              // L(J+1, J), the arithmetic lane J+1 does itself
+      rn = potrf_diag_pivot(R, J + 1, i, fma(-l1, l1, q));
+      if constexpr (J >= 1) R.a[J + 1] = fma(-lprev, Cp.v[J + 1], R.a[J + 1]);   // pending column J-1
+      const double t = fma(-lij, l1, R.a[J + 1]);
+      R.a[J + 1] = (i > J + 1) ? t : 0.0;
+      if constexpr (J + 2 < PB) {
+        un = shfl_d(R.a[J + 1], J + 2);
+        qn = shfl_d(R.dg, J + 2);
+      }
+    }
+    if (st && i > J) Mb[J * PLD + i] = lij;
+    if constexpr (J >= 1) potrf_diag_apply<J + 2>(R, Cp, lprev);   // the rest of pending column J-1
+    __syncwarp();
+    DiagCol Cn;
+    potrf_diag_fetch<J, J + 2>(Cn, Mb);
+    potrf_diag_step<J + 1>(R, Mb, i, st, rn, un, qn, Cn, lij);
+  }
+}
+// X = D^-1: lane c carries column c (x = e_c) through a right-looking forward substitution.  Column
+// K of D (contiguous in shared memory) is fetched one step ahead of its use, so the loads never
+// stall the single warp; the dependent chain is mul -> fma per column.
+template <int K, int I>
+__device__ __forceinline__ void potrf_diag_inv_apply(DiagRegs& R, const DiagCol& C) {
+  if constexpr (I < PB) {
+    R.x[I] = fma(-C.v[I], R.x[K], R.x[I]);
+    potrf_diag_inv_apply<K, I + 1>(R, C);
+  }
+}
+template <int K>
+__device__ __forceinline__ void potrf_diag_inv(DiagRegs& R, const double* Mb, const DiagCol& Cc) {
+  if constexpr (K < PB) {
+    DiagCol Cn;
+    if constexpr (K + 1 < PB) potrf_diag_fetch<K + 1, K + 2>(Cn, Mb);   // column K+1 below its diagonal
+    R.x[K] *= R.invd[K];
+    potrf_diag_inv_apply<K, K + 1>(R, Cc);
+    potrf_diag_inv<K + 1>(R, Mb, Cn);
+  }
+}
+template <int I>
+__device__ __forceinline__ void potrf_diag_inv_init(DiagRegs& R, int c) {
+  if constexpr (I < PB) {
+    R.x[I] = (I == c) ? 1.0 : 0.0;
+    potrf_diag_inv_init<I + 1>(R, c);
+  }
+}
+// X(J, c = i) -> M, entries above the diagonal go to a dump slot: an address select instead of a
+// predicate, because the compiler turns sixteen `if (J >= i)` stores into a divergent branch cascade
+template <int J>
+__device__ __forceinline__ void potrf_diag_store_x(const DiagRegs& R, double* Mb, double* dump, int i) {
+  if constexpr (J < PB) {
+    double* dst = (J >= i) ? Mb + (J + 1) * PLD + i : dump;
+    *dst = R.x[J];
+    potrf_diag_store_x<J + 1>(R, Mb, dump, i);
+  }
+}
+template <int J>
+__device__ __forceinline__ void potrf_diag_load(DiagRegs& R, const double* Mb, int i) {
+  if constexpr (J < PB) {
+    const double v = Mb[J * PLD + max(i, J)];                 // in-bounds for every lane
+    R.a[J] = (J < i) ? v : 0.0;
+    potrf_diag_load<J + 1>(R, Mb, i);
+  }
+}
+template <int J>
+__device__ __forceinline__ void potrf_diag_recips(DiagRegs& R) {   // invert-only path
+  if constexpr (J < PB) {
+    const double p = shfl_d(R.dg, J);
+    if (!(p > 0.0)) R.bad = min(R.bad, J);
+    R.invd[J] = 1.0 / p;
+    potrf_diag_recips<J + 1>(R);
+  }
+}
+template <bool FACTOR>
+__device__ __forceinline__ int potrf_diag_block(double* M, double* sdiag, double* dump, int k0, int lane) {
+  const int i = lane & 15;
+  const bool st = lane < PB;
+  double* Mb = M + k0 * PLD + k0;
+  DiagRegs R;
+  R.dg = Mb[i * PLD + i];
+  R.mydiag = R.dg;
+  R.bad = PB;
+  if constexpr (FACTOR) {
+    potrf_diag_load<0>(R, Mb, i);
+    POTRF_STAMP(40);
+    const double r0 = potrf_diag_pivot(R, 0, i, shfl_d(R.dg, 0));
+    const double u0 = shfl_d(R.a[0], 1), q0 = shfl_d(R.dg, 1);
+    DiagCol C0;
+#ifndef VC_POTRF_SKIP_FACTOR
+    potrf_diag_step<0>(R, Mb, i, st, r0, u0, q0, C0, 0.0);
+#endif
+    if (st) Mb[i * PLD + i] = R.mydiag;
+  } else {
+    potrf_diag_recips<0>(R);
+  }
+  __syncwarp();
+  POTRF_STAMP(41);
+#ifndef VC_POTRF_SKIP_INV
+  {
+    DiagCol C0;
+    potrf_diag_fetch<0, 1>(C0, Mb);
+    potrf_diag_inv_init<0>(R, i);
+    potrf_diag_inv<0>(R, Mb, C0);
+  }
+#endif
+  POTRF_STAMP(42);
+  if (st) {
+#ifndef VC_POTRF_SKIP_INV
+    potrf_diag_store_x<0>(R, Mb, dump + lane, i);
+#endif
+    sdiag[k0 + i] = R.mydiag;
+  }
+  return R.bad;
+}
+
+// helper-warp stores (threads ht = 0 .. nh-1): one 16-column block of L, one 16-row block of the inverse
+__device__ __forceinline__ void potrf_store_L_cols(const double* M, double* At, int64_t lda, int kb, int ht, int nh) {
+  const int c0 = kb * PB, r0 = kb * PB;                     // rows r0 .. 127, columns c0 .. c0+15
+  const int nr2 = (TILE - r0) / 2;
+  for (int idx = ht; idx < nr2 * PB; idx += nh) {
+    const int r = r0 + 2 * (idx % nr2), c = c0 + idx / nr2;
+    if (r >= c) *reinterpret_cast<double2*>(At + r + (int64_t)c * lda) = *reinterpret_cast<const double2*>(M + c * PLD + r);
+    else if (r + 1 == c) At[r + 1 + (int64_t)c * lda] = M[c * PLD + r + 1];
+  }
+}
+__device__ __forceinline__ void potrf_store_X_rows(const double* M, double* linv, int bi, int hw, int nhw, int lane) {
+  // 16 (rows) x 4 (columns) patches, 16 bytes per lane: four full 128-byte lines per store.  Only the
+  // block columns <= bi are written (the buffer is zero-filled once when it is allocated); the upper
+  // half of the diagonal block is written as zeros.
+  const int r = PB * bi + 2 * (lane & 7);
+  for (int pt = hw; pt < 4 * (bi + 1); pt += nhw) {
+    const int c = 4 * pt + (lane >> 3);
+    double2 v;
+    v.x = (r >= c) ? M[(r + 1) * PLD + c] : 0.0;
+    v.y = (r + 1 >= c) ? M[(r + 2) * PLD + c] : 0.0;
+    *reinterpret_cast<double2*>(linv + r + TILE * c) = v;
+  }
+}
+
+template <bool FACTOR>
+__global__ void __launch_bounds__(POTRF_THREADS, 1)
+k_potrf128c(double* __restrict__ At, int64_t lda, int jt, double* __restrict__ linv_all,
+            double* __restrict__ logdet_part, int* __restrict__ info) {
+  extern __shared__ __align__(16) double M[];
+  double* sdiag = M + (TILE + 1) * PLD;
+  double* scratch = sdiag + TILE;
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, tig = lane & 3;
+  double* ss = scratch + warp * PB * SS_LD;
+  double* linv = linv_all + (int64_t)jt * TILE * TILE;
+  POTRF_STAMP(0);
+
+  // load: 16-byte async copies, first block column as its own group so that the first diagonal
+  // block can start before the rest of the tile has arrived.  Chunks that straddle the diagonal
+  // bring one upper-triangle word along; it lands on a slot of the inverse that is written before
+  // it is ever read.
+  for (int idx = tid; idx < (TILE / 2) * PB; idx += POTRF_THREADS) {
+    const int r = (idx & 63) * 2, c = idx >> 6;
+    if (r + 1 >= c) cp_async16(M + c * PLD + r, At + r + (int64_t)c * lda);
+  }
+  cp_async_commit();
+  for (int idx = tid + (TILE / 2) * PB; idx < TILE * TILE / 2; idx += POTRF_THREADS) {
+    const int r = (idx & 63) * 2, c = idx >> 6;
+    if (r + 1 >= c) cp_async16(M + c * PLD + r, At + r + (int64_t)c * lda);
+  }
+  cp_async_commit();
+  cp_async_wait<1>();
+  __syncthreads();
+  POTRF_STAMP(1);
+
+  for (int kb = 0; kb < TILE / PB; ++kb) {
+    const int k0 = kb * PB;
+    // phase 1: the previous rank-16 update on the next diagonal block only (pairs 0, 1, 2)
+    if (FACTOR && kb > 0) {
+      if (warp < 3) potrf_update_pair(M, k0 - PB, warp, g, tig);
+      __syncthreads();
+    }
+    POTRF_STAMP(2 + 4 * kb);
+    // phase 2: warp 0 factors + inverts the diagonal block; the others finish update kb-1, assemble
+    // block row kb-1 of the inverse and write finished parts of L and of the inverse to global memory
+    if (warp == 0) {
+      const int bad = potrf_diag_block<FACTOR>(M, sdiag, ss, k0, lane);
+      if (bad < PB && lane == 0) atomicMin(info, jt * TILE + k0 + bad + 1);
+      POTRF_STAMP(3 + 4 * kb);
+    } else if (kb > 0) {
+      const int nxr = kb - 1;
+      const int nsubp = (TILE - k0) / 8;                    // 8-row sub-tiles behind block column kb-1
+      const int nitems = nxr + (FACTOR ? nsubp * (nsubp + 1) / 2 - 3 : 0);
+      // stores first: they drain while the DMMA items below run
+      if (FACTOR) potrf_store_L_cols(M, At, lda, kb - 1, tid - 32, POTRF_THREADS - 32);
+      if (kb > 1) potrf_store_X_rows(M, linv, kb - 2, warp - 1, 7, lane);
+      for (int t = warp - 1; t < nitems; t += 7) {
+        if (t < nxr) potrf_xrow_item(M, ss, kb - 1, t, g, tig);
+        else potrf_update_pair(M, k0 - PB, t - nxr + 3, g, tig);
+      }
+    }
+    if (kb == 0) cp_async_wait<0>();                        // the rest of the tile (every thread its own copies)
+    __syncthreads();
+    POTRF_STAMP(4 + 4 * kb);
+    // phase 3: panel solve  P = A * Dinv^T  on rows [k0+16, 128)
+    if (FACTOR) {
+      const int nsub = (TILE - k0 - PB) / 8;
+      for (int ms = warp; ms < nsub; ms += 8) {
+        const int row0 = k0 + PB + 8 * ms;
+        double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+#pragma unroll
+        for (int k4 = 0; k4 < 4; ++k4) {
+          const int k = 4 * k4 + tig;
+          const double af = M[(k0 + k) * PLD + row0 + g];
+#pragma unroll
+          for (int nn = 0; nn < 2; ++nn) {
+            const int c = 8 * nn + g;
+            const double bf = (k <= c) ? M[(k0 + c + 1) * PLD + k0 + k] : 0.0;
+            dmma884(acc[nn][0], acc[nn][1], af, bf);
+          }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int nn = 0; nn < 2; ++nn) {
+          M[(k0 + 8 * nn + 2 * tig) * PLD + row0 + g] = acc[nn][0];
+          M[(k0 + 8 * nn + 2 * tig + 1) * PLD + row0 + g] = acc[nn][1];
+        }
+      }
+      __syncthreads();
+    }
+    POTRF_STAMP(5 + 4 * kb);
+  }
+  // last block row of the inverse
+  if (warp < TILE / PB - 1) potrf_xrow_item(M, ss, TILE / PB - 1, warp, g, tig);
+  __syncthreads();
+  POTRF_STAMP(34);
+
+  // ---- what is left to write: the last block column of L, the last two block rows of the inverse ----
+  if (FACTOR) potrf_store_L_cols(M, At, lda, TILE / PB - 1, tid, POTRF_THREADS);
+  POTRF_STAMP(35);
+  potrf_store_X_rows(M, linv, TILE / PB - 2, warp, POTRF_THREADS / 32, lane);
+  potrf_store_X_rows(M, linv, TILE / PB - 1, warp, POTRF_THREADS / 32, lane);
+  POTRF_STAMP(36);
+  if (tid < 32) {
+    double sl = 0.0;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) sl += log(sdiag[lane * 4 + a]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sl += __shfl_xor_sync(0xffffffffu, sl, o);
+    if (lane == 0) logdet_part[jt] = sl;
+  }
+}
+
 // copy K panel columns (local column lcol0..) of the listed row tiles into a tile-major buffer:
 // tile I -> dst + (I - tile0) * 128 * K, column-major inside with ld 128 (distributed driver)
 __global__ void __launch_bounds__(256) k_pack_tiles(GemmArgs p, const int* __restrict__ tiles, int lcol0, int K,
@@ -744,7 +1174,15 @@ void vc_chol_init() {
   VC_CUDA_TRY(cudaFuncSetAttribute(k_potrf128, cudaFuncAttributeMaxDynamicSharedMemorySize, POTRF_SMEM));
   VC_CUDA_TRY(cudaFuncSetAttribute(k_potrf128b<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, POTRFB_SMEM));
   VC_CUDA_TRY(cudaFuncSetAttribute(k_potrf128b<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, POTRFB_SMEM));
+  VC_CUDA_TRY(cudaFuncSetAttribute(k_potrf128c<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, POTRFC_SMEM));
+  VC_CUDA_TRY(cudaFuncSetAttribute(k_potrf128c<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, POTRFC_SMEM));
   done = true;
+}
+
+// VC_POTRF_B=1: the previous blocked diagonal-tile kernel instead of k_potrf128c (A/B runs)
+static bool potrf_use_b() {
+  static const bool b = getenv("VC_POTRF_B") != nullptr;
+  return b;
 }
 
 // inverse of every diagonal tile of a factor that is already resident (no factorisation)
@@ -752,7 +1190,8 @@ void vc_chol_invert_diag_tiles(const VcMatrix& M, VcCholWork& w, int64_t* launch
   vc_launch_reset_info(w.info, w.st_main, launches);
   for (int jt = 0; jt < M.nt; ++jt) {
     double* diag = M.a + (int64_t)jt * TILE * (M.lda + 1);
-    k_potrf128b<false><<<1, POTRF_THREADS, POTRFB_SMEM, w.st_main>>>(diag, M.lda, jt, w.linv, w.logdet_part, w.info);
+    if (potrf_use_b()) k_potrf128b<false><<<1, POTRF_THREADS, POTRFB_SMEM, w.st_main>>>(diag, M.lda, jt, w.linv, w.logdet_part, w.info);
+    else k_potrf128c<false><<<1, POTRF_THREADS, POTRFC_SMEM, w.st_main>>>(diag, M.lda, jt, w.linv, w.logdet_part, w.info);
     ++*launches;
   }
 }
@@ -764,21 +1203,72 @@ void vc_chol_free_plans(VcCholWork& w) {
   w.plan_solve = VcCholPlan();
 }
 
+// ---------------------------------------------------------------------------------------------
+// Timeline tracing (development aid): VC_TRACE=<file> brackets every factorisation kernel with CUDA
+// events on its own stream and appends "kernel stream arg0 arg1 start_us end_us" lines per
+// factorisation.  Off by default; the events cost ~1-2 us per launch when on.
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct TraceRec { const char* name; uintptr_t stream; int a, b; cudaEvent_t e0, e1; };
+struct Tracer {
+  bool on = false;
+  std::string path;
+  std::vector<TraceRec> recs;
+  Tracer() {
+    const char* p = getenv("VC_TRACE");
+    if (p && *p) { on = true; path = p; }
+  }
+};
+Tracer& tracer() { static Tracer t; return t; }
+struct TraceScope {
+  cudaStream_t st; bool on;
+  TraceScope(const char* name, cudaStream_t s, int a, int b) : st(s), on(tracer().on) {
+    if (!on) return;
+    TraceRec r{name, (uintptr_t)s, a, b, nullptr, nullptr};
+    cudaEventCreate(&r.e0); cudaEventCreate(&r.e1);
+    cudaEventRecord(r.e0, s);
+    tracer().recs.push_back(r);
+  }
+  ~TraceScope() { if (on) cudaEventRecord(tracer().recs.back().e1, st); }
+};
+void trace_dump(int nt, int nb) {
+  Tracer& t = tracer();
+  if (!t.on || t.recs.empty()) return;
+  cudaDeviceSynchronize();
+  FILE* f = fopen(t.path.c_str(), "a");
+  if (f) fprintf(f, "# factorisation nt=%d nb=%d launches=%zu\n", nt, nb, t.recs.size());
+  for (auto& r : t.recs) {
+    float a = 0.f, b = 0.f;
+    cudaEventElapsedTime(&a, t.recs[0].e0, r.e0);
+    cudaEventElapsedTime(&b, t.recs[0].e0, r.e1);
+    if (f) fprintf(f, "%s %llx %d %d %.2f %.2f\n", r.name, (unsigned long long)r.stream, r.a, r.b, a * 1e3, b * 1e3);
+  }
+  for (auto& r : t.recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+  if (f) fclose(f);
+  t.recs.clear();
+}
+}  // namespace
+
 void vc_launch_potrf(double* diag, int64_t lda, int jt, double* linv_all, double* logdet_part, int* info,
                      bool legacy, cudaStream_t st, int64_t* launches) {
+  TraceScope ts("potrf", st, jt, 1);
   if (legacy) k_potrf128<<<1, POTRF_THREADS, POTRF_SMEM, st>>>(diag, lda, jt, linv_all, logdet_part, info);
-  else k_potrf128b<true><<<1, POTRF_THREADS, POTRFB_SMEM, st>>>(diag, lda, jt, linv_all, logdet_part, info);
+  else if (potrf_use_b()) k_potrf128b<true><<<1, POTRF_THREADS, POTRFB_SMEM, st>>>(diag, lda, jt, linv_all, logdet_part, info);
+  else k_potrf128c<true><<<1, POTRF_THREADS, POTRFC_SMEM, st>>>(diag, lda, jt, linv_all, logdet_part, info);
   ++*launches;
 }
 void vc_launch_trsm(const VcGemmArgs& g, int grid, cudaStream_t st, int64_t* launches) {
   if (grid <= 0) return;
+  TraceScope ts("trsm", st, g.jt, grid);
   k_trsm_panel<<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(g);
   ++*launches;
 }
 void vc_launch_syrk(const VcGemmArgs& g, int num_sms, bool legacy, cudaStream_t st, int64_t* launches) {
   if (g.ntiles <= 0) return;
+  const int grid = legacy ? g.ntiles : std::min(g.ntiles, std::max(num_sms, 1));
+  TraceScope ts(g.K == TILE ? "syrk128" : "syrk", st, g.ntiles, grid);
   if (legacy) k_syrk_tiles<<<g.ntiles, GEMM_THREADS, GEMM_SMEM, st>>>(g);
-  else k_syrk_ws<<<std::min(g.ntiles, std::max(num_sms, 1)), WS_THREADS, WS_SMEM, st>>>(g);
+  else k_syrk_ws<<<grid, WS_THREADS, WS_SMEM, st>>>(g);
   ++*launches;
 }
 void vc_launch_reset_info(int* info, cudaStream_t st, int64_t* launches) {
@@ -887,6 +1377,7 @@ void vc_chol_factor(const VcMatrix& M, VcCholWork& w, int64_t* launches, int mod
       panel(ob);
       if (oe < nt) launch_update(M, w, pl, first_call[ob / nb] + (size_t)(oe - ob), sm, launches);
     }
+    trace_dump(nt, nb);
     return;
   }
   // Lookahead, software-pipelined over the outer blocks:
@@ -921,6 +1412,7 @@ void vc_chol_factor(const VcMatrix& M, VcCholWork& w, int64_t* launches, int mod
     }
   }
   VC_CUDA_TRY(cudaStreamWaitEvent(sm, w.ev_panel, 0));
+  trace_dump(nt, nb);
 }
 
 // ---------------------------------------------------------------------------------------------
