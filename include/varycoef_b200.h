@@ -63,7 +63,7 @@ typedef struct vc_config {
   int32_t taper_id;      /* VC_TAPER_*; control$tapering != NULL  */
   int32_t device;        /* CUDA device ordinal */
   double  taper_range;   /* control$tapering (delta) */
-  int32_t nb_outer;      /* outer Cholesky block (multiple of 128; 0 = auto: 256 / 512 / 1024 by n) */
+  int32_t nb_outer;      /* outer Cholesky block (multiple of 128; 0 = auto: 128 / 256 / 512 / 1024 by n) */
   int32_t flags;         /* VC_FLAG_* */
 } vc_config;
 

@@ -141,7 +141,8 @@ vc_handle* vc_alloc_common(const vc_config* cfg, int64_t n, int d, int p, int q,
       h->cw.num_sms = prop.multiProcessorCount;
     }
     // outer block: measured best 256 for n <= 12k, 512 up to 40k, 1024 beyond (profiles/r01_block_sweep.md)
-    const int nb_auto = np >= 40000 ? 1024 : (np <= 12288 ? 256 : 512);
+    // measured (profiles/r01_block_sweep.md, r01_panel_chain.md): 128 up to n = 4096, 256 up to 12288, 512, 1024 from 40000
+    const int nb_auto = np >= 40000 ? 1024 : (np <= 4096 ? 128 : (np <= 12288 ? 256 : 512));
     h->cw.nb_tiles = (cfg->nb_outer > 0 ? cfg->nb_outer : nb_auto) / VC_TILE;
     h->cw.lookahead = !(cfg->flags & VC_FLAG_NO_LOOKAHEAD);
     h->cw.st_main = h->st_main; h->cw.st_panel = h->st_panel;
