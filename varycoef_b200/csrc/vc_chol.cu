@@ -187,7 +187,7 @@ __device__ __forceinline__ void gemm_mainloop(const double* __restrict__ Ag, int
 __global__ void __launch_bounds__(GEMM_THREADS, 1) k_trsm_panel(GemmArgs p) {
   extern __shared__ __align__(16) double smem[];
   const int I = p.tiles ? (p.tiles[blockIdx.x] & 0xffff)
-                        : (((int)blockIdx.x < p.n_main) ? p.jt + 1 + blockIdx.x : p.nt + (blockIdx.x - p.n_main));
+                        : (((int)blockIdx.x < p.n_main) ? p.jt + 1 + p.i_skip + blockIdx.x : p.nt + (blockIdx.x - p.n_main));
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
   const int wm = warp & 1, wn = warp >> 1;
@@ -241,6 +241,110 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_syrk_tiles(GemmArgs p) {
       c[0] = c[0] + (-acc[i][j][0]);
       c[ldc] = c[ldc] + (-acc[i][j][1]);
     }
+}
+
+// ---- 32-row strips of ONE tile: the tiles on the critical path --------------------------------
+// The chain potrf(j) -> TRSM of row tile j+1 -> update of tile (j+1, j+1) -> potrf(j+1) bounds a
+// factorisation at n <= 10 000.  A whole 128x128x128 product costs 16.7 us on one SM whatever the
+// kernel; cut into four 32-row strips on four SMs it costs a quarter.  Same per-element DMMA order as
+// the full-tile kernels, so results are bit-identical.  Block b: tile b / 4, strip b % 4.
+constexpr int STRIP = 32;
+__device__ __forceinline__ void warp_stage_strip(const double* sa, const double* sb, int tig, double (&acc)[4][2][2]) {
+#pragma unroll
+  for (int k4 = 0; k4 < KC / 4; ++k4) {
+    const int kk = (k4 * 4 + tig) * SLD;
+    double a[4], b[2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a[i] = sa[kk + i * 8];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) b[j] = sb[kk + j * 8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+  }
+}
+// acc[i][j][0..1]: rows i*8 + (lane>>2) of the strip, cols warp*16 + j*8 + 2*(lane&3) + {0,1}
+__device__ __forceinline__ void strip_mainloop(const double* __restrict__ Ag, int64_t lda_a,
+                                               const double* __restrict__ Bg, int64_t lda_b, int K,
+                                               double (&acc)[4][2][2], double* smem) {
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, tig = lane & 3;
+  const int nk = K / KC;
+  auto load_stage = [&](int slot, int kt) {
+    double* sa = smem + slot * STAGE_DOUBLES;
+    double* sb = sa + KC * SLD;
+    {
+      const int col = tid >> 4, rc = (tid & 15) * 2;          // 16 k-columns x 32 rows of the strip
+      cp_async16(sa + col * SLD + rc, Ag + (int64_t)(kt * KC + col) * lda_a + rc);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int id = tid + GEMM_THREADS * i;
+      const int col = id >> 6, rc = (id & 63) * 2;
+      cp_async16(sb + col * SLD + rc, Bg + (int64_t)(kt * KC + col) * lda_b + rc);
+    }
+  };
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; ++s) {
+    if (s < nk) load_stage(s, s);
+    cp_async_commit();
+  }
+  for (int kt = 0; kt < nk; ++kt) {
+    cp_async_wait<STAGES - 2>();
+    __syncthreads();
+    const int nxt = kt + STAGES - 1;
+    if (nxt < nk) load_stage(nxt % STAGES, nxt);
+    cp_async_commit();
+    const double* sa = smem + (kt % STAGES) * STAGE_DOUBLES;
+    warp_stage_strip(sa + g, sa + KC * SLD + warp * 16 + g, tig, acc);
+  }
+  cp_async_wait<0>();
+  __syncthreads();
+}
+template <bool TRSM>
+__global__ void __launch_bounds__(GEMM_THREADS, 1) k_strip(GemmArgs p) {
+  extern __shared__ __align__(16) double smem[];
+  const int t = blockIdx.x >> 2, s = blockIdx.x & 3;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, tig = lane & 3;
+  double acc[4][2][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+  if (TRSM) {   // main row tile jt + 1 + i_skip + t:  X = A * Linv^T, in place (a strip reads only its own rows)
+    int64_t ld;
+    double* Ct = c_tile_ptr(p, p.jt + 1 + p.i_skip + t, p.jt, ld) + STRIP * s;
+    strip_mainloop(Ct, ld, p.linv, TILE, TILE, acc, smem);
+    double* cbase = Ct + g + (int64_t)(warp * 16 + 2 * tig) * ld;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        double* c = cbase + i * 8 + (int64_t)(j * 8) * ld;
+        c[0] = acc[i][j][0];
+        c[ld] = acc[i][j][1];
+      }
+  } else {      // C(I, J) -= P_I P_J^T
+    const int packed = p.tiles[t];
+    const int I = packed & 0xffff, J = packed >> 16;
+    int64_t ldc, ldpi, ldpj;
+    double* Ct = c_tile_ptr(p, I, J, ldc) + STRIP * s;
+    const double* Pi = op_ptr(p, p.src_a, I, 0, ldpi) + STRIP * s;
+    const double* Pj = op_ptr(p, p.src_b, J, 0, ldpj);
+    strip_mainloop(Pi, ldpi, Pj, ldpj, p.K, acc, smem);
+    double* cbase = Ct + g + (int64_t)(warp * 16 + 2 * tig) * ldc;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        double* c = cbase + i * 8 + (int64_t)(j * 8) * ldc;
+        red_add_f64(c, -acc[i][j][0]);
+        red_add_f64(c + ldc, -acc[i][j][1]);
+      }
+  }
 }
 
 // ---- update, persistent + warp-specialised ----------------------------------------------------
@@ -1170,6 +1274,8 @@ void vc_chol_init() {
   if (done) return;
   VC_CUDA_TRY(cudaFuncSetAttribute(k_trsm_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
   VC_CUDA_TRY(cudaFuncSetAttribute(k_syrk_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+  VC_CUDA_TRY(cudaFuncSetAttribute(k_strip<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+  VC_CUDA_TRY(cudaFuncSetAttribute(k_strip<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
   VC_CUDA_TRY(cudaFuncSetAttribute(k_syrk_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM));
   VC_CUDA_TRY(cudaFuncSetAttribute(k_potrf128, cudaFuncAttributeMaxDynamicSharedMemorySize, POTRF_SMEM));
   VC_CUDA_TRY(cudaFuncSetAttribute(k_potrf128b<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, POTRFB_SMEM));
@@ -1197,6 +1303,8 @@ void vc_chol_invert_diag_tiles(const VcMatrix& M, VcCholWork& w, int64_t* launch
 }
 
 void vc_chol_free_plans(VcCholWork& w) {
+  for (auto& e : w.ev_aux) { if (e) cudaEventDestroy(e); e = nullptr; }
+  if (w.st_aux) { cudaStreamDestroy(w.st_aux); w.st_aux = nullptr; }
   if (w.plan_factor.tiles_dev) cudaFree(w.plan_factor.tiles_dev);
   if (w.plan_solve.tiles_dev) cudaFree(w.plan_solve.tiles_dev);
   w.plan_factor = VcCholPlan();
@@ -1265,11 +1373,34 @@ void vc_launch_trsm(const VcGemmArgs& g, int grid, cudaStream_t st, int64_t* lau
 }
 void vc_launch_syrk(const VcGemmArgs& g, int num_sms, bool legacy, cudaStream_t st, int64_t* launches) {
   if (g.ntiles <= 0) return;
-  const int grid = legacy ? g.ntiles : std::min(g.ntiles, std::max(num_sms, 1));
-  TraceScope ts(g.K == TILE ? "syrk128" : "syrk", st, g.ntiles, grid);
-  if (legacy) k_syrk_tiles<<<g.ntiles, GEMM_THREADS, GEMM_SMEM, st>>>(g);
-  else k_syrk_ws<<<grid, WS_THREADS, WS_SMEM, st>>>(g);
-  ++*launches;
+  if (legacy) {
+    TraceScope ts(g.K == TILE ? "syrk128" : "syrk", st, g.ntiles, g.ntiles);
+    k_syrk_tiles<<<g.ntiles, GEMM_THREADS, GEMM_SMEM, st>>>(g);
+    ++*launches;
+    return;
+  }
+  const int grid = std::min(g.ntiles, std::max(num_sms, 1));
+  // A persistent grid walks ntiles / grid tiles per CTA; a remainder of a few tiles costs a whole extra
+  // tile time on an almost empty machine.  Run a small remainder as 32-row strips instead (a quarter of
+  // the time, same arithmetic).  VC_NO_STRIPS=1 disables.
+  static const bool no_strips = getenv("VC_NO_STRIPS") != nullptr;
+  const int rem = g.ntiles % grid;
+  const int tail = (!no_strips && g.ntiles > grid && rem > 0 && 100 * rem <= 45 * grid) ? rem : 0;
+  VcGemmArgs m = g;
+  m.ntiles = g.ntiles - tail;
+  {
+    TraceScope ts(g.K == TILE ? "syrk128" : "syrk", st, m.ntiles, grid);
+    k_syrk_ws<<<grid, WS_THREADS, WS_SMEM, st>>>(m);
+    ++*launches;
+  }
+  if (tail > 0) {
+    VcGemmArgs t = g;
+    t.tiles = g.tiles + m.ntiles;
+    t.ntiles = tail;
+    TraceScope ts("utail", st, tail, 4 * tail);
+    k_strip<false><<<4 * tail, GEMM_THREADS, GEMM_SMEM, st>>>(t);
+    ++*launches;
+  }
 }
 void vc_launch_reset_info(int* info, cudaStream_t st, int64_t* launches) {
   k_reset_info<<<1, 1, 0, st>>>(info);
@@ -1380,20 +1511,96 @@ void vc_chol_factor(const VcMatrix& M, VcCholWork& w, int64_t* launches, int mod
     trace_dump(nt, nb);
     return;
   }
+  // Critical-first scheduling (default; VC_NO_STRIPS=1 restores the plain panel order): the tiles on the
+  // chain potrf(j) -> TRSM(row tile j+1) -> update(tile (j+1, j+1)) -> potrf(j+1) are computed in four
+  // 32-row strips on sp, everything else of the panel (other row tiles, rest of the inner update) runs
+  // on a third stream sq and only has to be back before the next TRSM.
+  static const bool no_strips = getenv("VC_NO_STRIPS") != nullptr;
+  // measured: pays up to n ~ 6000 (the chain bounds the evaluation); beyond, the trailing update does and
+  // the extra launches / reserved SMs cost 1-2 %
+  const bool split = !w.legacy_syrk && !no_strips && nt <= 48;
+  cudaStream_t sq = sp;
+  cudaEvent_t ev_p = nullptr, ev_t = nullptr, ev_u = nullptr, ev_q = nullptr, ev_c0 = nullptr;
+  if (split) {
+    if (!w.st_aux) {
+      VC_CUDA_TRY(cudaStreamCreateWithFlags(&w.st_aux, cudaStreamNonBlocking));
+      for (auto& e : w.ev_aux) VC_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    sq = w.st_aux;
+    ev_p = w.ev_aux[0]; ev_t = w.ev_aux[1]; ev_u = w.ev_aux[2]; ev_q = w.ev_aux[3]; ev_c0 = w.ev_aux[4];
+  }
+  auto strip_update = [&](size_t call, cudaStream_t st) {       // first tile of a plan call, in strips
+    const VcUpdateCall& c = pl.calls[call];
+    GemmArgs g = base_args(M);
+    g.k0 = c.k0; g.K = c.K; g.tiles = pl.tiles_dev + c.tile_off; g.ntiles = 1;
+    TraceScope ts("ustrip", st, 1, 4);
+    k_strip<false><<<4, GEMM_THREADS, GEMM_SMEM, st>>>(g);
+    ++*launches;
+  };
+  // wait_ev: the columns of this block have received every earlier update (nullptr for the first block)
+  auto panel_split = [&](int ob, cudaEvent_t wait_ev) {
+    const int oe = std::min(ob + nb, nt);
+    size_t call = first_call[ob / nb];
+    cudaEvent_t pending = wait_ev;
+    if (wait_ev) VC_CUDA_TRY(cudaStreamWaitEvent(sq, wait_ev, 0));
+    for (int jt = ob; jt < oe; ++jt) {
+      double* diag = M.a + (int64_t)jt * TILE * (M.lda + 1);
+      vc_launch_potrf(diag, M.lda, jt, w.linv, w.logdet_part, w.info, w.legacy_potrf, sp, launches);
+      VC_CUDA_TRY(cudaEventRecord(ev_p, sp));
+      VC_CUDA_TRY(cudaStreamWaitEvent(sq, ev_p, 0));
+      if (pending) {
+        VC_CUDA_TRY(cudaStreamWaitEvent(sp, pending, 0));
+        pending = nullptr;
+      }
+      GemmArgs g = base_args(M);
+      g.linv = w.linv + (int64_t)jt * TILE * TILE;
+      g.k0 = jt * TILE; g.K = TILE; g.jt = jt;
+      const int n_main = nt - (jt + 1);
+      if (n_main > 0) {                                          // row tile jt+1, four strips, on sp
+        TraceScope ts("tstrip", sp, jt, 4);
+        k_strip<true><<<4, GEMM_THREADS, GEMM_SMEM, sp>>>(g);
+        ++*launches;
+      }
+      g.i_skip = 1;                                              // the other row tiles + border, on sq
+      g.n_main = std::max(n_main - 1, 0);
+      vc_launch_trsm(g, g.n_main + nbt, sq, launches);
+      const VcUpdateCall& c = pl.calls[call];
+      if (c.ntiles > 0) {                                        // inner update: tile (jt+1, jt+1) first
+        strip_update(call, sp);
+        VC_CUDA_TRY(cudaEventRecord(ev_t, sp));
+        VC_CUDA_TRY(cudaStreamWaitEvent(sq, ev_t, 0));
+        launch_update(M, w, pl, call, sq, launches, 0, 1, c.ntiles - 1);
+        VC_CUDA_TRY(cudaEventRecord(ev_u, sq));
+        pending = ev_u;
+      }
+      ++call;
+    }
+    VC_CUDA_TRY(cudaEventRecord(ev_q, sq));                      // the panel is complete when both streams are
+    VC_CUDA_TRY(cudaStreamWaitEvent(sp, ev_q, 0));
+  };
   // Lookahead, software-pipelined over the outer blocks:
   //   sm:  col(s) | rest A(s) on num_sms - R CTAs ............ | rest B(s) on every SM | col(s+1) ...
   //   sp:          panel(s+1): potrf / TRSM / inner updates ---^ (rest B and col(s+1) wait for it)
   // The next panel only touches columns [oe, ne), which the rest update neither reads nor writes.
-  panel(0);
+  if (split) panel_split(0, nullptr); else panel(0);
   VC_CUDA_TRY(cudaEventRecord(w.ev_panel, sp));
   for (int ob = 0; ob < nt; ob += nb) {
     const int oe = std::min(ob + nb, nt);
     if (oe >= nt) break;
     const size_t c_col = first_call[ob / nb] + (size_t)(oe - ob), c_rest = c_col + 1;
     VC_CUDA_TRY(cudaStreamWaitEvent(sm, w.ev_panel, 0));
-    launch_update(M, w, pl, c_col, sm, launches);
+    if (split) {
+      // column update: the next diagonal tile first (strips), so that its potrf starts at once
+      strip_update(c_col, sm);
+      VC_CUDA_TRY(cudaEventRecord(ev_c0, sm));
+      VC_CUDA_TRY(cudaStreamWaitEvent(sp, ev_c0, 0));
+      // leave a few SMs free: potrf(oe) and the TRSM strips must not queue behind a full-machine grid
+      launch_update(M, w, pl, c_col, sm, launches, 5, 1, pl.calls[c_col].ntiles - 1);
+    } else {
+      launch_update(M, w, pl, c_col, sm, launches);
+    }
     VC_CUDA_TRY(cudaEventRecord(w.ev_col, sm));
-    VC_CUDA_TRY(cudaStreamWaitEvent(sp, w.ev_col, 0));
+    if (!split) VC_CUDA_TRY(cudaStreamWaitEvent(sp, w.ev_col, 0));
     const int rest_tiles = pl.calls[c_rest].ntiles;
     int nA = rest_tiles;
     int reserve = w.legacy_syrk ? 0 : vc_pick_reserved_sms(w.num_sms, nt + nbt - oe, nb, rest_tiles, &nA);
@@ -1404,7 +1611,7 @@ void vc_chol_factor(const VcMatrix& M, VcCholWork& w, int64_t* launches, int mod
       if (nosplit) nA = rest_tiles;
     }
     launch_update(M, w, pl, c_rest, sm, launches, reserve, 0, nA);
-    panel(oe);
+    if (split) panel_split(oe, w.ev_col); else panel(oe);
     VC_CUDA_TRY(cudaEventRecord(w.ev_panel, sp));
     if (nA < rest_tiles) {
       VC_CUDA_TRY(cudaStreamWaitEvent(sm, w.ev_panel, 0));

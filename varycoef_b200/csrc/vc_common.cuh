@@ -102,6 +102,7 @@ struct VcGemmArgs {       // by-value argument block of k_trsm_panel / k_syrk_ws
   const int* tiles;       // packed (I | J << 16), global tile indices
   int ntiles;
   VcOpSrc src_a, src_b;   // operand sources of the update kernels
+  int i_skip;             // TRSM without tile list: main row tiles start at jt + 1 + i_skip
 };
 struct VcUpdateCall {     // one trailing / inner update of the factorisation plan
   int k0, K;             // panel columns [k0, k0 + K)
@@ -127,6 +128,9 @@ struct VcCholWork {
   cudaStream_t st_main, st_panel;
   cudaEvent_t ev_panel, ev_update, ev_col;
   VcCholPlan plan_factor, plan_solve;
+  // critical-first scheduling (created on first use, released by vc_chol_free_plans)
+  cudaStream_t st_aux = nullptr;
+  cudaEvent_t ev_aux[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 enum { VC_SWEEP_FACTOR = 0,   // potrf + TRSM + updates on every row tile (main + border)
        VC_SWEEP_SOLVE = 1,    // factor already resident: only the border rows are swept
