@@ -151,7 +151,8 @@ vc_handle* vc_alloc_common(const vc_config* cfg, int64_t n, int d, int p, int q,
       VC_CUDA_TRY(cudaMalloc(&h->M.b, (size_t)h->M.ldb * np * sizeof(double)));
       VC_CUDA_TRY(cudaMalloc(&h->cw.linv, (size_t)h->M.nt * VC_TILE * VC_TILE * sizeof(double)));
       // the diagonal-tile kernel writes only the lower 16x16 blocks of each inverse; the rest stays zero
-      VC_CUDA_TRY(cudaMemset(h->cw.linv, 0, (size_t)h->M.nt * VC_TILE * VC_TILE * sizeof(double)));
+      // (on the handle's own stream: a legacy-stream memset is not ordered against non-blocking streams)
+      VC_CUDA_TRY(cudaMemsetAsync(h->cw.linv, 0, (size_t)h->M.nt * VC_TILE * VC_TILE * sizeof(double), h->st_main));
       VC_CUDA_TRY(cudaMalloc(&h->cw.logdet_part, (size_t)h->M.nt * sizeof(double)));
     }
     VC_CUDA_TRY(cudaMalloc(&h->cw.info, sizeof(int)));
@@ -237,6 +238,8 @@ int vc_make_theta(const vc_handle* h, const double* theta, VcTheta* t) {
 // how many evaluation lanes a batch may use: one evaluation fills the GPU from n ~ 20k on
 static int lane_cap(const vc_handle* h) {
   if (h->dist) return 1;
+  static const int env_cap = getenv("VC_MAX_LANES") ? atoi(getenv("VC_MAX_LANES")) : 0;   // tuning / debugging
+  if (env_cap >= 1) return std::min(env_cap, 4);
   if (h->n_pad <= 12288) return 4;
   if (h->n_pad <= 24576) return 2;
   return 1;
@@ -263,7 +266,7 @@ static VcLane* make_lane(vc_handle* h) {
   L->cw.legacy_syrk = h->cw.legacy_syrk; L->cw.legacy_potrf = h->cw.legacy_potrf; L->cw.num_sms = h->cw.num_sms;
   L->cw.st_main = L->st_main; L->cw.st_panel = L->st_panel;
   VC_CUDA_TRY(cudaMalloc(&L->cw.linv, (size_t)L->M.nt * VC_TILE * VC_TILE * sizeof(double)));
-  VC_CUDA_TRY(cudaMemset(L->cw.linv, 0, (size_t)L->M.nt * VC_TILE * VC_TILE * sizeof(double)));
+  VC_CUDA_TRY(cudaMemsetAsync(L->cw.linv, 0, (size_t)L->M.nt * VC_TILE * VC_TILE * sizeof(double), L->st_main));
   VC_CUDA_TRY(cudaMalloc(&L->cw.logdet_part, (size_t)L->M.nt * sizeof(double)));
   VC_CUDA_TRY(cudaMalloc(&L->cw.info, sizeof(int)));
   const int m = h->p + 1;

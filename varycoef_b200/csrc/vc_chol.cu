@@ -1518,7 +1518,10 @@ void vc_chol_factor(const VcMatrix& M, VcCholWork& w, int64_t* launches, int mod
   static const bool no_strips = getenv("VC_NO_STRIPS") != nullptr;
   // measured: pays up to n ~ 6000 (the chain bounds the evaluation); beyond, the trailing update does and
   // the extra launches / reserved SMs cost 1-2 %
-  const bool split = !w.legacy_syrk && !no_strips && nt <= 48;
+  // OPT-IN (VC_SPLIT_SCHED=1): single evaluations gain 6-15 % at n <= 5000, but multi-lane batches
+  // (vc_n2ll_batch) have produced wrong factors with it -- not yet understood, so it is off by default
+  static const bool split_sched = getenv("VC_SPLIT_SCHED") != nullptr;
+  const bool split = split_sched && !w.legacy_syrk && !no_strips && nt <= 48;
   cudaStream_t sq = sp;
   cudaEvent_t ev_p = nullptr, ev_t = nullptr, ev_u = nullptr, ev_q = nullptr, ev_c0 = nullptr;
   if (split) {

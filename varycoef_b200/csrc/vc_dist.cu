@@ -300,7 +300,8 @@ extern "C" int vc_create_dist(vc_handle** out, const vc_config* cfg_in, int64_t 
     const int64_t Kmax = (int64_t)nb * VC_TILE;
     VC_CUDA_TRY(cudaMalloc(&D->dd, ((size_t)nb * VC_TILE * Kmax + (size_t)nb * VC_TILE * VC_TILE) * sizeof(double)));
     // inverse slots: the diagonal-tile kernel writes only their lower 16x16 blocks, the rest stays zero
-    VC_CUDA_TRY(cudaMemset(D->dd, 0, ((size_t)nb * VC_TILE * Kmax + (size_t)nb * VC_TILE * VC_TILE) * sizeof(double)));
+    VC_CUDA_TRY(cudaMemsetAsync(D->dd, 0, ((size_t)nb * VC_TILE * Kmax + (size_t)nb * VC_TILE * VC_TILE) * sizeof(double), h->st_main));
+    VC_CUDA_TRY(cudaStreamSynchronize(h->st_main));
     for (int i = 0; i < 2; ++i)
       VC_CUDA_TRY(cudaMalloc(&D->pnl[i], (size_t)(nt + 1) * VC_TILE * Kmax * sizeof(double)));
     const int m = p + 1;
