@@ -210,3 +210,16 @@ def test_graft_entry_build_and_reference_arm_json():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["value"] > 0
     assert d["metric"].startswith("-2logL evals/sec")
+
+
+def test_split_schedule_model_has_no_unordered_conflicts():
+    """tools/schedule_model.py mirrors the host calls of the opt-in critical-first schedule (vc_chol.cu, panel_split):
+    every pair of kernels with conflicting tile accesses must be ordered by stream order or an event; dropping any of
+    the waits must be detected."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import schedule_model as sm
+    for nt, nb in [(5, 1), (6, 2), (7, 3)]:
+        for frac in (None, 0.5):
+            assert sm.factor_split(nt, nb, 1, frac, 2).check() == []
+    for drop in ("sq_ev_col", "sp_pending", "join", "ev_c0", "ev_t"):
+        assert sm.factor_split(7, 3, 1, 0.5, 1, drop).check() != [], drop
