@@ -769,16 +769,6 @@ __device__ long long g_potrf_clk[64];
 #define POTRF_STAMP(k) do { } while (0)
 #endif
 
-// 1 / sqrt(s) to ~1 ulp (s > 0); NaN / inf for s <= 0 so that a bad pivot poisons what follows
-__device__ __forceinline__ double rsqrt_newton(double s) {
-  double y;
-  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(s));
-  const double hs = 0.5 * s;
-  y = y * fma(-hs * y, y, 1.5);
-  y = y * fma(-hs * y, y, 1.5);
-  return y;
-}
-
 // rank-16 update of the 8x8 pair t of the trailing lower triangle behind block column k0 / 16
 __device__ __forceinline__ void potrf_update_pair(double* M, int k0, int t, int g, int tig) {
   int sa = (int)((sqrtf(8.0f * t + 1.0f) - 1.0f) * 0.5f);
