@@ -1526,6 +1526,11 @@ void vc_chol_factor(const VcMatrix& M, VcCholWork& w, int64_t* launches, int mod
     const VcUpdateCall& c = pl.calls[call];
     GemmArgs g = base_args(M);
     g.k0 = c.k0; g.K = c.K; g.tiles = pl.tiles_dev + c.tile_off; g.ntiles = 1;
+    static const bool no_ustrip = getenv("VC_SPLIT_NO_USTRIP") != nullptr;       // diagnostics
+    if (no_ustrip) {
+      vc_launch_syrk(g, 1, false, st, launches);
+      return;
+    }
     TraceScope ts("ustrip", st, 1, 4);
     k_strip<false><<<4, GEMM_THREADS, GEMM_SMEM, st>>>(g);
     ++*launches;
@@ -1550,9 +1555,16 @@ void vc_chol_factor(const VcMatrix& M, VcCholWork& w, int64_t* launches, int mod
       g.k0 = jt * TILE; g.K = TILE; g.jt = jt;
       const int n_main = nt - (jt + 1);
       if (n_main > 0) {                                          // row tile jt+1, four strips, on sp
-        TraceScope ts("tstrip", sp, jt, 4);
-        k_strip<true><<<4, GEMM_THREADS, GEMM_SMEM, sp>>>(g);
-        ++*launches;
+        static const bool no_tstrip = getenv("VC_SPLIT_NO_TSTRIP") != nullptr;   // diagnostics
+        if (no_tstrip) {
+          GemmArgs g1 = g;
+          g1.n_main = 1;
+          vc_launch_trsm(g1, 1, sp, launches);
+        } else {
+          TraceScope ts("tstrip", sp, jt, 4);
+          k_strip<true><<<4, GEMM_THREADS, GEMM_SMEM, sp>>>(g);
+          ++*launches;
+        }
       }
       g.i_skip = 1;                                              // the other row tiles + border, on sq
       g.n_main = std::max(n_main - 1, 0);
