@@ -341,8 +341,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_strip(GemmArgs p) {
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
         double* c = cbase + i * 8 + (int64_t)(j * 8) * ldc;
-        red_add_f64(c, -acc[i][j][0]);
-        red_add_f64(c + ldc, -acc[i][j][1]);
+        if (p.n_main == 1) {   // exclusive owner of the tile (critical-first schedule): load + store, same rounding
+          __stcg(c, __ldcg(c) + (-acc[i][j][0]));
+          __stcg(c + ldc, __ldcg(c + ldc) + (-acc[i][j][1]));
+        } else {
+          red_add_f64(c, -acc[i][j][0]);
+          red_add_f64(c + ldc, -acc[i][j][1]);
+        }
       }
   }
 }
@@ -1526,6 +1531,8 @@ void vc_chol_factor(const VcMatrix& M, VcCholWork& w, int64_t* launches, int mod
     const VcUpdateCall& c = pl.calls[call];
     GemmArgs g = base_args(M);
     g.k0 = c.k0; g.K = c.K; g.tiles = pl.tiles_dev + c.tile_off; g.ntiles = 1;
+    static const bool ldst = getenv("VC_SPLIT_LDST") != nullptr;                  // diagnostics: no RED on this tile
+    g.n_main = ldst ? 1 : 0;
     static const bool no_ustrip = getenv("VC_SPLIT_NO_USTRIP") != nullptr;       // diagnostics
     if (no_ustrip) {
       vc_launch_syrk(g, 1, false, st, launches);
