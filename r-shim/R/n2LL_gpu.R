@@ -27,3 +27,12 @@ n2LL <- function(x, cov_func, outer.W, y, X, W, mean.est = NULL, taper = NULL,
 #   - gpu <- vcb_handle(y, X, locs, W, control)
 #   - pass `gpu = gpu` in the optim()/optimParallel() argument list and in `args` of extract_fun
 #   - med_dist: median of the pairwise distances still needed for default bounds (host, once)
+
+# After the optimisation (R-pkg/R/SVC_mle.R:205-296) the O(n^3) post-processing also comes from the resident factor:
+#   post <- .Call(C_vcb_post, gpu, cov.par, p, TRUE)      # list(mu_GLS, Sigma_FE = (X' S^-1 X)^-1, edof)
+#     replaces solve(Sigma_final) in prep_par_output (utils.R:423-473) and eff_dof() (eff_dof.R:7-21)
+#   pr <- .Call(C_vcb_predict, gpu, cov.par, mu, newlocs, newX, newW, q, compute.y.var)
+#     replaces the body of predict.SVC_mle (predict-SVC_mle.R:80-267): list(eff, y.pred, y.var)
+# SVC_selection: CD_mu's  R.t.inv <- solve(t(R)); X.tilde <- R.t.inv %*% X  (SVC_selection.R:30-35) becomes
+#   .Call(C_vcb_n2ll, gpu, theta.k, rep(0, p)); Z <- .Call(C_vcb_whitened, gpu, n, p)   # cbind(X.tilde, y.tilde)
+GLS_chol.matrix <- function(R, X, y) as.numeric(.Call(C_vcb_gls_chol, R, as.matrix(X), as.numeric(y), 0L))

@@ -61,6 +61,7 @@ SEXP vcb_n2ll(SEXP ext, SEXP theta, SEXP mu) {
                    &val, REAL(mu_out), &logdet, &quad);
   vcb_check(rc, h);
   SEXP out = PROTECT(Rf_ScalarReal(val));
+  Rf_setAttrib(out, Rf_install("mu"), mu_out);       /* first p entries are the mean used (GLS estimate or mu) */
   Rf_setAttrib(out, Rf_install("logdet"), Rf_ScalarReal(logdet));
   Rf_setAttrib(out, Rf_install("quad"), Rf_ScalarReal(quad));
   UNPROTECT(2);
@@ -80,10 +81,75 @@ SEXP vcb_n2ll_batch(SEXP ext, SEXP thetas, SEXP mus) {
   return out;
 }
 
+/* .Call(C_vcb_post, handle, theta, p, want_edof) -> list(mu, Sigma_FE, edof): the O(n^3) pieces of
+ * prep_par_output (R-pkg/R/utils.R:423-473) and eff_dof (R-pkg/R/eff_dof.R:7-21) from the resident factor */
+SEXP vcb_post(SEXP ext, SEXP theta, SEXP p_, SEXP want_edof) {
+  vc_handle* h = vcb_get(ext);
+  const int p = Rf_asInteger(p_);
+  SEXP mu = PROTECT(Rf_allocVector(REALSXP, p));
+  SEXP sfe = PROTECT(Rf_allocMatrix(REALSXP, p, p));
+  double edof = NA_REAL;
+  int rc = vc_post(h, REAL(theta), REAL(mu), REAL(sfe), Rf_asLogical(want_edof) ? &edof : NULL);
+  vcb_check(rc, h);
+  SEXP out = PROTECT(Rf_allocVector(VECSXP, 3));
+  SET_VECTOR_ELT(out, 0, mu);
+  SET_VECTOR_ELT(out, 1, sfe);
+  SET_VECTOR_ELT(out, 2, Rf_ScalarReal(edof));
+  UNPROTECT(3);
+  return out;
+}
+
+/* .Call(C_vcb_predict, handle, theta, mu, newlocs, newX or NULL, newW or NULL, q, y_var) ->
+ * list(eff[n_new x q], y_pred or NULL, y_var or NULL): predict.SVC_mle (R-pkg/R/predict-SVC_mle.R:80-267) */
+SEXP vcb_predict(SEXP ext, SEXP theta, SEXP mu, SEXP newlocs, SEXP newX, SEXP newW, SEXP q_, SEXP want_var) {
+  vc_handle* h = vcb_get(ext);
+  const int64_t n_new = Rf_nrows(newlocs);
+  const int q = Rf_asInteger(q_);
+  const int have_xw = !Rf_isNull(newX) && !Rf_isNull(newW);
+  const int var = have_xw && Rf_asLogical(want_var);
+  SEXP eff = PROTECT(Rf_allocMatrix(REALSXP, (int) n_new, q));
+  SEXP yp = PROTECT(have_xw ? Rf_allocVector(REALSXP, n_new) : R_NilValue);
+  SEXP yv = PROTECT(var ? Rf_allocVector(REALSXP, n_new) : R_NilValue);
+  int rc = vc_predict(h, REAL(theta), REAL(mu), n_new, REAL(newlocs), have_xw ? REAL(newX) : NULL,
+                      have_xw ? REAL(newW) : NULL, REAL(eff), have_xw ? REAL(yp) : NULL, var ? REAL(yv) : NULL);
+  vcb_check(rc, h);
+  SEXP out = PROTECT(Rf_allocVector(VECSXP, 3));
+  SET_VECTOR_ELT(out, 0, eff);
+  SET_VECTOR_ELT(out, 1, yp);
+  SET_VECTOR_ELT(out, 2, yv);
+  UNPROTECT(4);
+  return out;
+}
+
+/* .Call(C_vcb_whitened, handle, n, p) -> solve(t(R), cbind(X, y)) of the last evaluation: what CD_mu needs
+ * (R-pkg/R/SVC_selection.R:30-35) without forming solve(t(R)) */
+SEXP vcb_whitened(SEXP ext, SEXP n_, SEXP p_) {
+  vc_handle* h = vcb_get(ext);
+  SEXP Z = PROTECT(Rf_allocMatrix(REALSXP, Rf_asInteger(n_), Rf_asInteger(p_) + 1));
+  vcb_check(vc_get_whitened(h, REAL(Z)), h);
+  UNPROTECT(1);
+  return Z;
+}
+
+/* .Call(C_vcb_gls_chol, R, X, y, device) -> mu: GLS_chol.matrix (R-pkg/R/utils.R:93-101) */
+SEXP vcb_gls_chol(SEXP R, SEXP X, SEXP y, SEXP device) {
+  const int p = Rf_ncols(X);
+  SEXP mu = PROTECT(Rf_allocVector(REALSXP, p));
+  int rc = vc_gls_chol(Rf_asInteger(device), (int64_t) Rf_nrows(X), p, REAL(R), REAL(X), REAL(y), REAL(mu));
+  if (rc == VC_ERR_INVALID) Rf_error("GLS_chol: R must be an upper Cholesky factor with a positive diagonal");
+  if (rc != VC_OK) Rf_error("varycoef_b200 (%d): %s", rc, vc_last_error(NULL));
+  UNPROTECT(1);
+  return mu;
+}
+
 static const R_CallMethodDef vcb_calls[] = {
   {"C_vcb_create", (DL_FUNC) &vcb_create, 10},
   {"C_vcb_n2ll", (DL_FUNC) &vcb_n2ll, 3},
   {"C_vcb_n2ll_batch", (DL_FUNC) &vcb_n2ll_batch, 3},
+  {"C_vcb_post", (DL_FUNC) &vcb_post, 4},
+  {"C_vcb_predict", (DL_FUNC) &vcb_predict, 8},
+  {"C_vcb_whitened", (DL_FUNC) &vcb_whitened, 3},
+  {"C_vcb_gls_chol", (DL_FUNC) &vcb_gls_chol, 4},
   {NULL, NULL, 0}
 };
 

@@ -223,3 +223,16 @@ def test_split_schedule_model_has_no_unordered_conflicts():
             assert sm.factor_split(nt, nb, 1, frac, 2).check() == []
     for drop in ("sq_ev_col", "sp_pending", "join", "ev_c0", "ev_t"):
         assert sm.factor_split(7, 3, 1, 0.5, 1, drop).check() != [], drop
+
+
+def test_r_shim_type_checks_against_the_header():
+    """The .Call shim a varycoef maintainer would add must at least type-check against
+    include/varycoef_b200.h; R itself is not in the image, r-shim/check/ holds a minimal stand-in of its C API."""
+    out = subprocess.run(["gcc", "-std=c99", "-fsyntax-only", "-I" + os.path.join(ROOT, "r-shim", "check"),
+                          "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "r-shim", "src", "varycoef_b200_r.c")],
+                         capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    src = open(os.path.join(ROOT, "r-shim", "src", "varycoef_b200_r.c")).read()
+    for fn in ("vc_create", "vc_n2ll", "vc_n2ll_batch", "vc_post", "vc_predict", "vc_get_whitened", "vc_gls_chol",
+               "vc_destroy", "vc_last_error", "vc_last_info"):
+        assert fn + "(" in src, fn
