@@ -236,3 +236,20 @@ def test_r_shim_type_checks_against_the_header():
     for fn in ("vc_create", "vc_n2ll", "vc_n2ll_batch", "vc_post", "vc_predict", "vc_get_whitened", "vc_gls_chol",
                "vc_destroy", "vc_last_error", "vc_last_info"):
         assert fn + "(" in src, fn
+
+
+def test_plain_c_client_links_and_validates_arguments(tmp_path):
+    """The drop-in boundary is a C ABI: a C99 program with no Python / torch in sight links against the library,
+    gets VC_ERR_INVALID for bad arguments and -- in this GPU-less container -- a loud VC_ERR_CUDA from vc_create."""
+    from varycoef_b200 import _build
+    lib = _build.build()
+    exe = str(tmp_path / "abi_client")
+    out = subprocess.run(["gcc", "-std=c99", "-I" + os.path.join(ROOT, "include"),
+                          os.path.join(ROOT, "tests", "c", "abi_client.c"), "-o", exe,
+                          "-L" + os.path.dirname(lib), "-lvarycoef_b200", "-lm",
+                          "-Wl,-rpath," + os.path.dirname(lib)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    run = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert run.returncode == 0, (run.returncode, run.stdout, run.stderr)
+    assert run.stdout.startswith("abi ")
+    assert ("no gpu:" in run.stdout) or ("n2ll " in run.stdout)
