@@ -7,21 +7,47 @@ One "step" = one evaluation of -2 logL (fused covariance build -> bordered DMMA 
 GLS / quadratic form / log-det) on synthetic sample_SVCdata-style inputs.  Default workload is the
 headline configuration C3 of BASELINE.json: n = 50 000, p = q = 3, exponential covariance, fp64.
 
-N > 1 (launched by torch.distributed.run, one rank per GPU): the objective shards across the
-finite-difference stencil optim evaluates -- every rank holds a replica of the O(n) inputs and
-evaluates its own theta; there is no collective on the data path ("scaling": "weak").
-The within-evaluation sharded path (n = 150k, 2D block-cyclic + NCCL) is `--workload c4`.
+N > 1 (launched by torch.distributed.run, one rank per GPU): the headline line is the objective sharded
+across the finite-difference stencil optim evaluates -- every rank holds a replica of the O(n) inputs
+and evaluates its own theta; no collective on the data path ("scaling": "weak").  After the timed
+region the same ranks also run the within-evaluation sharded path (C4: n = 150 000, p = q = 5, 2D
+block-cyclic + NCCL panel broadcasts) and report it in the `sharded` record, with its parity against
+the single-GPU path at n = 50 000.  `--workload c4` runs only that path as the headline.
 
-`--impl reference` times the reference's CPU op sequence (numpy/LAPACK restatement in oracle/,
-the reference itself is R and cannot run here) on the host cores, on a bounded sample.
+Outside the timed region, at N = 1: `parity` (C3 result vs an independent cuSOLVER factorisation of the
+GPU-built Sigma_y at n = 50 000), `library_bar` (cublasDgemm / cusolverDn potrf on this GPU),
+`cpu_baseline` (the reference's CPU op sequence on the host cores, bounded sample).
+
+`--impl reference` times the reference's CPU op sequence (numpy/LAPACK restatement in oracle/; the
+reference itself is R and cannot run here) on all host cores.  A step is one faithful evaluation at a
+bounded sample size n_s; `ms_per_step` is that measured time.  `value` (evals/s at the workload's n)
+is extrapolated with an exponent fitted to measured samples and flagged as such; the lean in-place
+sequence is measured once at the full n when host RAM allows (`cpu_baseline.lean_measured`).
 """
 from __future__ import annotations
 
+import os
+import sys
+
+
+def _host_threads() -> int:
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
+# The CPU arm must use every host core: torch.distributed.run exports OMP_NUM_THREADS=1 to its workers, which
+# silently made the N > 1 reference arm single-threaded.  Decide the BLAS thread count BEFORE numpy is imported.
+_WORLD = int(os.environ.get("WORLD_SIZE", "1"))
+if "reference" in sys.argv or _WORLD == 1:
+    _t = str(int(os.environ.get("VC_CPU_THREADS", "0")) or _host_threads())
+    for _k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_k] = _t
+
 import argparse
 import json
-import os
 import subprocess
-import sys
 import threading
 import time
 
@@ -41,6 +67,11 @@ os.dup2(2, 1)
 def emit(line: dict):
     _REAL_STDOUT.write(json.dumps(line) + "\n")
     _REAL_STDOUT.flush()
+
+
+def log(*a):
+    print("[bench]", *a, file=sys.stderr, flush=True)
+
 
 WORKLOADS = {
     # name: (n, p=q, cov, taper, seed offset, description)
@@ -90,6 +121,17 @@ def theta_stencil(n, p, q, L, y):
         true += [TRUE_SCALE[k], TRUE_VAR[k]]
     pts.append(np.array(true + [0.25]))
     return np.array(pts)
+
+
+def config_dict(workload, n, world):
+    """The `config` object: identical for the GPU arm and the reference arm of the same run."""
+    n0, p, cov, taper, _, desc = WORKLOADS[workload]
+    n_pad = (n + 127) // 128 * 128
+    return {"workload": desc, "n": n, "n_padded": n_pad, "p": p, "q": p, "cov": cov, "tapering": taper,
+            "mu_mode": "profile/GLS", "theta": "optim central-difference stencil around default init, cycled",
+            "parallelism": "theta-parallel replicas, no collective" if world > 1 else "single GPU",
+            "l2": "inputs larger than L2: every evaluation rewrites and refactors the %.1f GB matrix" % (
+                8.0 * n_pad * (n_pad + 128) / 1e9)}
 
 
 class ClockSampler:
@@ -143,17 +185,26 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU arm: the reference's op sequence (oracle port), bounded sample, extrapolated to the workload
+# CPU arm: the reference's op sequence (oracle port) on the host cores
 # ------------------------------------------------------------------------------------------------
+def blas_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        return int(max([i.get("num_threads", 1) for i in threadpool_info()] + [1]))
+    except Exception:
+        return int(os.environ.get("OMP_NUM_THREADS", "1"))
+
+
 def cpu_eval_timed(n_s, p, cov, seed_off, faithful=True):
     """One evaluation of the reference's dense n2LL op sequence at n_s on the host BLAS threads.
-    Returns (t_build, t_cubic): Sigma_y build (O(n^2)) and chol + solves + determinant (O(n^3))."""
+    Returns (t_build, t_cubic, t_dist, value): Sigma_y build (O(n^2)); chol + solves + determinant (O(n^3));
+    the distance matrix (once per fit in the reference: not charged to an evaluation)."""
     from oracle import svc_oracle as o
     locs, X, y, L = make_inputs(n_s, p, seed_off)
     th = theta_stencil(n_s, p, p, L, y)[0]
     t0 = time.perf_counter()
     D = o.own_dist(locs)
-    t_dist = time.perf_counter() - t0           # once per fit in the reference: not charged
+    t_dist = time.perf_counter() - t0
     t0 = time.perf_counter()
     S = o.sigma_y(th, D, X, cov)
     t_build = time.perf_counter() - t0
@@ -164,38 +215,120 @@ def cpu_eval_timed(n_s, p, cov, seed_off, faithful=True):
     return t_build, max(t_all - t_build, 1e-9), t_dist, v
 
 
-def cpu_arm(n, p, cov, seed_off, n_s, reps):
-    from threadpoolctl import threadpool_info
-    tb, tc = [], []
-    for _ in range(reps):
+def fit_power(ns, ts):
+    """least-squares fit of t = c n^e in log space"""
+    ln, lt = np.log(np.asarray(ns, float)), np.log(np.asarray(ts, float))
+    e, lc = np.polyfit(ln, lt, 1)
+    return float(np.exp(lc)), float(e)
+
+
+def extrapolate(samples, n):
+    """samples: list of (n_s, t_build, t_cubic).  Build scales as n^2 (measured at the largest sample);
+    the cubic part as c n^e with e the log-log slope between the two largest samples, clamped to [2, 3]
+    (e = 3 when only one size was measured)."""
+    samples = sorted(samples)
+    n_l, tb_l, tc_l = samples[-1]
+    if len({s[0] for s in samples}) >= 2:
+        # local slope between the two largest samples (small sizes are dominated by thread start-up and the
+        # single-threaded parts, which flattens a fit over all of them)
+        c, e = fit_power([s[0] for s in samples[-2:]], [s[2] for s in samples[-2:]])
+        e_used = min(max(e, 2.0), 3.0)      # asymptotically n^3; never extrapolate with a steeper or absurd slope
+    else:
+        e, e_used = 3.0, 3.0
+    t_cubic = tc_l * (n / n_l) ** e_used
+    t_build = tb_l * (n / n_l) ** 2
+    return t_build + t_cubic, {"fitted_exponent": e, "exponent_used": e_used,
+                               "samples": [{"n": s[0], "build_s": s[1], "cubic_s": s[2]} for s in samples]}
+
+
+def lean_full(n, p, cov, seed_off, threads):
+    """The lean in-place sequence measured at the full n (needs 8 n^2 bytes of host RAM)."""
+    from oracle.lean_inplace import n2ll_lean_inplace
+    try:
+        import psutil
+        avail = psutil.virtual_memory().available
+    except Exception:
+        avail = 0
+    need = 8.0 * n * n * 1.15 + 4e9
+    if avail < need:
+        return {"skipped": "host RAM available %.0f GB < %.0f GB needed" % (avail / 1e9, need / 1e9)}
+    locs, X, y, L = make_inputs(n, p, seed_off)
+    th = theta_stencil(n, p, p, L, y)[0]
+    t0 = time.perf_counter()
+    r = n2ll_lean_inplace(th, locs, X, X, y, cov, threads=threads)
+    wall = time.perf_counter() - t0
+    return {"n": n, "seconds": wall, "evals_per_s": 1.0 / wall, "build_s": r["t_build"], "dpotrf_s": r["t_chol"],
+            "solve_s": r["t_solve"], "dpotrf_gflops": n ** 3 / 3.0 / r["t_chol"] / 1e9, "n2ll": r["n2ll"],
+            "logdet": r["logdet"], "mu": [float(v) for v in r["mu"]], "theta": [float(v) for v in th],
+            "sequence": "blocked in-place build (lower) -> dpotrf -> dtrtrs -> sum log diag; numpy/OpenBLAS, %d threads" % threads}
+
+
+def cpu_arm_bounded(n, p, cov, seed_off, sizes):
+    """cpu_baseline of the GPU arm: ~10-30 s of CPU work -- the faithful sequence at two bounded sizes,
+    exponent fitted, extrapolated to n."""
+    samples = []
+    for n_s in sizes:
         b, c, _, _ = cpu_eval_timed(n_s, p, cov, seed_off, faithful=True)
-        tb.append(b); tc.append(c)
-    tb, tc = float(np.median(tb)), float(np.median(tc))
-    t_full = tb * (n / n_s) ** 2 + tc * (n / n_s) ** 3
-    threads = max([i.get("num_threads", 1) for i in threadpool_info()] + [1])
-    return {"value": 1.0 / t_full, "unit": UNIT, "cores": int(threads), "kind": "port",
-            "sample": ("faithful R op sequence (Sigma_y loop, dpotrf, 3x dgesv on the triangular factor, log-det) "
-                       "at n_s=%d, p=q=%d, %s: build %.3fs (x(n/n_s)^2) + cubic part %.3fs (x(n/n_s)^3) "
-                       "extrapolated to n=%d; host has %d logical cores"
-                       % (n_s, p, cov, tb, tc, n, os.cpu_count())),
-            "sample_seconds": tb + tc}
+        samples.append((n_s, b, c))
+    t_full, fit = extrapolate(samples, n)
+    return {"value": 1.0 / t_full, "unit": UNIT, "cores": blas_threads(), "kind": "port", "extrapolated": True,
+            "sample": ("faithful R op sequence (Sigma_y loop, dpotrf, 3x dgesv on the triangular factor, log-det) measured "
+                       "at n_s = %s, p=q=%d, %s; build x (n/n_s)^2, cubic part x (n/n_s)^%.2f (fitted %.2f) -> n=%d; host "
+                       "has %d usable cores" % ("/".join(str(s) for s in sizes), p, cov, fit["exponent_used"],
+                                                fit["fitted_exponent"], n, _host_threads())),
+            "sample_seconds": float(sum(s[1] + s[2] for s in samples)), "fit": fit}
 
 
 def run_reference(args):
     n, p, cov, taper, seed_off, desc = WORKLOADS[args.workload]
+    if args.n:
+        n = args.n
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    threads = blas_threads()
     n_s = args.cpu_sample_n
-    for _ in range(args.warmup if args.warmup < 2 else 1):
+    t_start = time.perf_counter()
+    for _ in range(max(0, args.warmup)):
         cpu_eval_timed(min(n_s, 2000), p, cov, seed_off)
-    t0 = time.perf_counter()
-    arm = cpu_arm(n, p, cov, seed_off, n_s, max(1, args.steps))
-    wall = time.perf_counter() - t0
+    K = max(1, args.steps)
+    tb, tc, step_s = [], [], []
+    for _ in range(K):
+        t0 = time.perf_counter()
+        b, c, t_dist, _ = cpu_eval_timed(n_s, p, cov, seed_off, faithful=True)
+        step_s.append(time.perf_counter() - t0 - t_dist)   # the distance matrix is per fit, not per evaluation
+        tb.append(b); tc.append(c)
+    samples = [(n_s, float(np.median(tb)), float(np.median(tc)))]
+    for n_f in args.cpu_fit_n:
+        if n_f and n_f != n_s:
+            b, c, _, _ = cpu_eval_timed(n_f, p, cov, seed_off, faithful=True)
+            samples.append((n_f, b, c))
+            log("reference: faithful sample n=%d build %.2fs cubic %.2fs" % (n_f, b, c))
+    t_full, fit = extrapolate(samples, n)
+    lean = None
+    if not args.no_lean_full:
+        try:
+            lean = lean_full(n, p, cov, seed_off, threads)
+            log("reference: lean at full n:", json.dumps(lean)[:300])
+        except Exception as e:  # noqa: BLE001
+            lean = {"skipped": "failed: %r" % (e,)}
+    arm = {"value": 1.0 / t_full, "unit": UNIT, "cores": threads, "kind": "port", "extrapolated": True,
+           "sample": ("each step = one faithful evaluation (Sigma_y loop, dpotrf, 3x dgesv on the triangular factor, "
+                      "log-det; R-pkg/R/objective_functions.R:4-62) at n_s=%d, p=q=%d, %s, %d BLAS threads: median build "
+                      "%.3fs + cubic part %.3fs.  value = 1 / (build x (n/n_l)^2 + cubic x (n/n_l)^%.2f) from the largest "
+                      "sample n_l=%d; exponent = log-log slope of the two largest of n_s in %s (fitted %.3f).  The faithful sequence cannot run at "
+                      "n=%d (needs (q+5) 8 n^2 B = %.0f GB)" % (
+                          n_s, p, cov, threads, samples[0][1], samples[0][2], fit["exponent_used"],
+                          max(s[0] for s in samples), sorted(s[0] for s in samples), fit["fitted_exponent"], n,
+                          (p + 5) * 8.0 * n * n / 1e9)),
+           "sample_seconds": float(np.mean(step_s)), "fit": fit, "lean_measured": lean}
+    wall = time.perf_counter() - t_start
     line = {"impl": "reference", "metric": METRIC, "value": arm["value"], "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / arm["value"],
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean(step_s)) * 1e3,
+            "ms_per_step_note": "measured: one faithful evaluation at the bounded sample size n_s=%d; `value` is the "
+                                "extrapolation to n=%d described in cpu_baseline.sample" % (n_s, n),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": {"workload": desc, "n": n, "p": p, "q": p, "cov": cov},
+            "data": "synthetic", "config": config_dict(args.workload, n, args.gpus),
             "cpu_baseline": arm,
             "e2e": {"value": arm["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "wall_s": wall}
@@ -205,6 +338,88 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
+def parity_record(obj, theta, X, y, local):
+    """C3 result vs an independent cuSOLVER/cuBLAS evaluation on the GPU-built Sigma_y (tools/third_path.py)."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from third_path import third_path_n2ll
+    ours = obj.n2LL(theta, parts=True)
+    ref = third_path_n2ll(obj, theta, X, y, local)
+    rel = abs(ours["n2ll"] - ref["n2ll"]) / abs(ref["n2ll"])
+    return {"against": "cuSOLVER potrf + cuBLAS trsm of the GPU-built Sigma_y (tools/third_path.py): independent "
+                       "factorisation, solves, GLS and log-det; the build kernel is shared (element-wise oracle tests)",
+            "n": obj.n, "theta": [float(v) for v in theta], "n2ll": ours["n2ll"], "n2ll_third_path": ref["n2ll"],
+            "rel": rel, "logdet_rel": abs(ours["logdet"] - ref["logdet"]) / abs(ref["logdet"]),
+            "quad_rel": abs(ours["quad"] - ref["quad"]) / abs(ref["quad"]),
+            "mu_rel": float(np.max(np.abs(ours["mu"] - ref["mu"])) / np.max(np.abs(ref["mu"]))),
+            "tolerance": 1e-10, "ok": bool(rel <= 1e-10),
+            "third_path_potrf_ms": ref["potrf_ms"]}
+
+
+def sharded_record(args, dist, world, rank, local, peak_tf, single_c3):
+    """Within-evaluation sharded path on the ranks of this run: C4 (n = 150 000, p = q = 5) timed, and its
+    parity against the single-GPU path at C3 (single_c3 = (theta, n2ll, logdet) computed before)."""
+    import torch
+    from varycoef_b200.dist import distributed_objective, process_grid
+    pr, pc = process_grid(world)
+    rec = {"grid": "%dx%d" % (pr, pc)}
+    # parity first (small): the same N-GPU driver at C3 vs the single-GPU value
+    n3, p3, cov3, _, so3, _ = WORKLOADS["c3"]
+    locs, X, y, L = make_inputs(n3, p3, so3)
+    theta3, v_single, ld_single = single_c3
+    obj = distributed_objective(y, X, locs, cov_name=cov3, profileLik=True, device=local)
+    r = obj.n2LL(theta3, parts=True)
+    obj.close()
+    rec["parity_n"] = n3
+    rec["parity_n2ll_sharded"] = r["n2ll"]
+    rec["parity_n2ll_single_gpu"] = v_single
+    rec["parity_rel"] = abs(r["n2ll"] - v_single) / abs(v_single)
+    rec["parity_logdet_rel"] = abs(r["logdet"] - ld_single) / abs(ld_single)
+    del locs, X, y
+    # C4 timed
+    n, p, cov, _, so, desc = WORKLOADS["c4"]
+    if args.sharded_n:
+        n = args.sharded_n
+    locs, X, y, L = make_inputs(n, p, so)
+    thetas = theta_stencil(n, p, p, L, y)
+    obj = distributed_objective(y, X, locs, cov_name=cov, profileLik=True, device=local, nb_outer=args.nb)
+    Ks, Ws = args.sharded_steps, 1
+    for s in range(Ws):
+        obj.n2LL(thetas[s % len(thetas)])
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    dist.barrier(); torch.cuda.synchronize()
+    l0 = obj.launch_count
+    t0 = time.perf_counter()
+    phase = {"build_ms": 0.0, "chol_ms": 0.0, "finalize_ms": 0.0}
+    vals = []
+    for s in range(Ks):
+        vals.append(obj.n2LL(thetas[(Ws + s) % len(thetas)]))
+        tm = obj.timings()
+        for k in phase:
+            phase[k] += tm[k]
+    dist.barrier(); torch.cuda.synchronize()
+    elapsed = time.perf_counter() - t0
+    launches = obj.launch_count - l0
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([elapsed, float(launches)], dtype=torch.float64, device="cuda")
+    tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    elapsed, launches = float(tmax[0]), int(t[1].item())
+    obj.close()
+    chol_s = phase["chol_ms"] / Ks * 1e-3
+    rec.update({"workload": desc, "n": n, "p": p, "q": p, "cov": cov, "steps": Ks, "warmup": Ws,
+                "evals_per_s": Ks / elapsed, "ms_per_eval": elapsed / Ks * 1e3, "scaling": "strong",
+                "tflops": n ** 3 / 3.0 / chol_s / 1e12, "peak_tflops": peak_tf * world,
+                "frac": n ** 3 / 3.0 / chol_s / 1e12 / (peak_tf * world) if peak_tf > 0 else None,
+                "peak_source": "N x fp64 DMMA probe of rank 0 (vc_probe_dmma_peak)",
+                "phases_ms": {k: v / Ks for k, v in phase.items()}, "gpu_launches": launches, "clocks": clocks,
+                "n2ll_sample": vals[:2],
+                "nvlink_bytes_per_rank_bound": 8.0 * n * n * (1.0 / pr + 1.0 / pc) / 2.0,
+                "parallelism": "2D block-cyclic Sigma_y, NCCL panel broadcasts, lookahead"})
+    return rec
+
+
 def run_ours(args):
     import torch
     import ctypes as C
@@ -294,12 +509,43 @@ def run_ours(args):
         launches_total = int(ph[3].item())
     else:
         launches_total = launches
+
+    # ---- records outside the timed region ----
+    extra = {}
+    at_size = (n == WORKLOADS[args.workload][0])
+    if world == 1 and not args.no_parity:
+        try:
+            extra["parity"] = parity_record(obj, thetas[0], X, y, local)
+        except Exception as e:  # noqa: BLE001
+            extra["parity"] = {"failed": repr(e)}
+        torch.cuda.empty_cache()
+    single_c3 = None
+    if world > 1 and not args.no_sharded and args.workload == "c3" and at_size:
+        r0 = obj.n2LL(thetas[0], parts=True)
+        single_c3 = (thetas[0], r0["n2ll"], r0["logdet"])
+    n_pad = obj.padded_n
+    obj.close()
+    del obj
+    torch.cuda.empty_cache()
+    if world == 1 and not args.no_library_bar:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            from third_path import library_bar
+            extra["library_bar"] = library_bar(n, local)
+        except Exception as e:  # noqa: BLE001
+            extra["library_bar"] = {"failed": repr(e)}
+        torch.cuda.empty_cache()
+    if single_c3 is not None:
+        try:
+            extra["sharded"] = sharded_record(args, dist, world, rank, local, peak_tf.value, single_c3)
+        except Exception as e:  # noqa: BLE001
+            extra["sharded"] = {"failed": repr(e)}
+            log("sharded record failed on rank %d: %r" % (rank, e))
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
 
-    n_pad = obj.padded_n
     chol_s = phase["chol_ms"] / K * 1e-3
     build_s = phase["build_ms"] / K * 1e-3
     chol_flops = n ** 3 / 3.0
@@ -314,17 +560,17 @@ def run_ours(args):
     roof = {"bound": "tensor", "kernel": "k_syrk_ws (persistent TMA-fed DMMA trailing SYRK) inside the bordered Cholesky",
             "achieved": chol_flops / chol_s / 1e12, "peak": peak_tf.value, "unit": "TFLOP/s",
             "frac": chol_flops / chol_s / 1e12 / peak_tf.value if peak_tf.value > 0 else None,
-            "traffic": NCU_TRAFFIC_BYTES.get(args.workload) if n == WORKLOADS[args.workload][0] else None,
+            "traffic": NCU_TRAFFIC_BYTES.get(args.workload) if at_size else None,
             "traffic_note": "DRAM read + write bytes of all Cholesky kernels of ONE evaluation (per evaluation, like "
                             "`achieved`), ncu dram__bytes_{read,write}.sum, profiles/r01_traffic_n50k.md: 616 GB in "
                             "1.21 s = 8 % of DRAM peak -- the factorisation is DMMA-bound (pipe 95.7 % active in "
                             "k_syrk_ws, profiles/r01_syrk_ws_n20k.md); the C trapezoid alone accounts for ~400 GB",
             "peak_source": "fp64 DMMA m8n8k4 register-resident probe measured live on this GPU (vc_probe_dmma_peak); "
-                           "MEASURED_PEAKS.json has no fp64 entry",
+                           "MEASURED_PEAKS.json has no fp64 entry; see library_bar.dgemm_tflops for cuBLAS on the same GPU",
             "algorithmic": "n^3/3 flops per evaluation / CUDA-event time of the whole factorisation (panels included)"}
     roof_build = {"bound": "hbm", "kernel": "k_build_fast (fused distance + covariance)", "achieved": build_bytes / build_s / 1e9,
                   "peak": hbm_peak, "unit": "GB/s", "frac": build_bytes / build_s / 1e9 / hbm_peak,
-                  "traffic": NCU_BUILD_TRAFFIC_BYTES.get(args.workload) if n == WORKLOADS[args.workload][0] else None, "peak_source": hbm_src,
+                  "traffic": NCU_BUILD_TRAFFIC_BYTES.get(args.workload) if at_size else None, "peak_source": hbm_src,
                   "algorithmic": "4 n (n+1) bytes written (lower triangle) / CUDA-event time of build + border"}
     h2d = 8 * n * (2 + p + q + 1) + 8 * (2 * q + 1)
     d2h = 8 * 132
@@ -332,11 +578,7 @@ def run_ours(args):
         "metric": METRIC, "value": K * world / elapsed, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
         "ms_per_step": elapsed / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": desc, "n": n, "n_padded": n_pad, "p": p, "q": q, "cov": cov, "tapering": taper,
-                   "mu_mode": "profile/GLS", "theta": "optim central-difference stencil around default init, cycled",
-                   "parallelism": "theta-parallel replicas, no collective" if world > 1 else "single GPU",
-                   "l2": "inputs larger than L2: every evaluation rewrites and refactors the %.1f GB matrix" % (
-                       8.0 * n_pad * (n_pad + 128) / 1e9)},
+        "config": config_dict(args.workload, n, world),
         "clocks": clocks,
         "e2e": {"value": K * world / elapsed_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": launches_total,
@@ -344,19 +586,21 @@ def run_ours(args):
         "phases_ms": {k: v / K for k, v in phase.items()},
         "n2ll_sample": vals[:2],
     }
+    line.update(extra)
     if world == 1 and not args.no_cpu:
-        line["cpu_baseline"] = cpu_arm(n, p, cov, seed_off, args.cpu_sample_n, 1)
+        line["cpu_baseline"] = cpu_arm_bounded(n, p, cov, seed_off, args.cpu_bounded_n)
     emit(line)
-    obj.close()
     if dist is not None:
         dist.destroy_process_group()
 
 
 def run_dist(args):
     """--workload c4: ONE evaluation sharded 2D block-cyclic over all ranks (n = 150 000 does not fit
-    one GPU).  value = whole-job evaluations per second; strong scaling in N."""
+    one GPU in full storage).  value = whole-job evaluations per second; strong scaling in N."""
     import torch
     import torch.distributed as dist
+    import ctypes as C
+    from varycoef_b200 import _lib
     from varycoef_b200.dist import distributed_objective, process_grid
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -375,6 +619,8 @@ def run_dist(args):
     locs, X, y, L = make_inputs(n, p, seed_off)
     thetas = theta_stencil(n, p, q, L, y)
     K, Wm = args.steps, args.warmup
+    peak_tf = C.c_double(0.0)
+    _lib.lib().vc_probe_dmma_peak(local, 20000, C.byref(peak_tf))
     obj = distributed_objective(y, X, locs, cov_name=cov, profileLik=True, device=local, nb_outer=args.nb)
     for s in range(Wm):
         obj.n2LL(thetas[s % len(thetas)])
@@ -405,6 +651,7 @@ def run_dist(args):
         if os.environ.get("VC_GRID"):
             pr, pc = (int(v) for v in os.environ["VC_GRID"].split("x"))
         chol_s = phase["chol_ms"] / K * 1e-3
+        peak = peak_tf.value * world
         line = {"metric": "-2logL evals/sec (fp64), one evaluation sharded 2D block-cyclic", "value": K / elapsed,
                 "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": elapsed / K * 1e3,
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -415,9 +662,9 @@ def run_dist(args):
                 "e2e": {"value": K / elapsed, "unit": UNIT, "h2d_bytes_per_step": 8 * (2 * q + 1), "d2h_bytes_per_step": 8 * 132,
                         "note": "inputs are O(n) and resident; theta in, scalar out through the public API"},
                 "roofline": {"bound": "tensor", "kernel": "k_syrk_ws across %d GPUs" % world,
-                             "achieved": n ** 3 / 3.0 / chol_s / 1e12, "peak": 37.0 * world, "unit": "TFLOP/s",
-                             "frac": n ** 3 / 3.0 / chol_s / 1e12 / (37.0 * world), "traffic": None,
-                             "peak_source": "N x 37.0 TFLOP/s fp64 DMMA probe (vc_probe_dmma_peak)"},
+                             "achieved": n ** 3 / 3.0 / chol_s / 1e12, "peak": peak, "unit": "TFLOP/s",
+                             "frac": n ** 3 / 3.0 / chol_s / 1e12 / peak if peak > 0 else None, "traffic": None,
+                             "peak_source": "N x fp64 DMMA probe of rank 0 (vc_probe_dmma_peak)"},
                 "phases_ms": {k: v / K for k, v in phase.items()}, "n2ll_sample": vals[:2]}
         emit(line)
     obj.close()
@@ -432,8 +679,18 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--n", "--problem-n", dest="n", type=int, default=0, help="override n (debug; use --problem-n under torchrun)")
-    ap.add_argument("--cpu-sample-n", type=int, default=6000)
+    ap.add_argument("--cpu-sample-n", type=int, default=6000, help="reference arm: size of one step's faithful evaluation")
+    ap.add_argument("--cpu-fit-n", type=lambda s: [int(v) for v in s.split(",") if v], default=[3000, 12000],
+                    help="reference arm: extra faithful sample sizes (once each) for the fitted exponent")
+    ap.add_argument("--cpu-bounded-n", type=lambda s: [int(v) for v in s.split(",") if v], default=[4000, 8000],
+                    help="GPU arm: sizes of the bounded cpu_baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-lean-full", action="store_true", help="reference arm: skip the lean in-place run at full n")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-library-bar", action="store_true")
+    ap.add_argument("--no-sharded", action="store_true", help="N > 1: skip the sharded (C4) record")
+    ap.add_argument("--sharded-n", type=int, default=0, help="override n of the sharded record (debug)")
+    ap.add_argument("--sharded-steps", type=int, default=2)
     ap.add_argument("--nb", type=int, default=0, help="outer Cholesky block (0 = auto)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -116,6 +116,9 @@ VC_API int vc_n2ll_batch(vc_handle* h, int32_t m, const double* thetas, int32_t 
 
 /* Sigma_y(theta) (R-pkg/R/utils.R:171-233) as a full symmetric n x n column-major matrix (parity/debug) */
 VC_API int vc_sigma(vc_handle* h, const double* theta, double* out);
+/* the same matrix written to DEVICE memory of the handle's GPU (n x n column-major, ld = n): lets a caller
+ * hand Sigma_y to another device library (cuSOLVER, as the parity tests do at n = 50 000) without a host trip */
+VC_API int vc_sigma_device(vc_handle* h, const double* theta, double* out_dev);
 
 /*
  * Cholesky factor of the last successful evaluation, as base::chol returns it:

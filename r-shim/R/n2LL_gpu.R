@@ -10,7 +10,9 @@ vcb_handle <- function(y, X, locs, W, control) {
   taper_id <- if (is.null(control$tapering)) 0L else
     switch(control$cov.name, exp = 1L, mat32 = 1L, mat52 = 2L,
            stop("tapering undefined for this covariance"))       # get_taper, utils.R:545-552
-  .Call(C_vcb_create, as.matrix(locs), as.matrix(X), as.matrix(W), as.numeric(y),
+  locs <- as.matrix(locs); X <- as.matrix(X); W <- as.matrix(W)
+  storage.mode(locs) <- storage.mode(X) <- storage.mode(W) <- "double"   # integer grids / dummies
+  .Call(C_vcb_create, locs, X, W, as.numeric(y),
         cov_id, dist_id, if (is.null(control$dist$p)) 2 else control$dist$p,
         taper_id, if (is.null(control$tapering)) 0 else control$tapering, 0L)
 }
@@ -19,7 +21,7 @@ n2LL <- function(x, cov_func, outer.W, y, X, W, mean.est = NULL, taper = NULL,
                  pc.dens = NULL, Rstruct = NULL, profile = TRUE, gpu = NULL) {
   q <- dim(W)[2]; p <- dim(X)[2]
   mu <- if (profile) mean.est else x[1 + 2*q + 1:p]     # NULL -> GLS on the GPU
-  as.numeric(.Call(C_vcb_n2ll, gpu, x[1:(2*q+1)], mu)) + pc_penalty(x, q, pc.dens)
+  as.numeric(.Call(C_vcb_n2ll, gpu, x[1:(2*q+1)], mu, p)) + pc_penalty(x, q, pc.dens)
 }
 
 # In MLE_computation (R-pkg/R/SVC_mle.R:12-242) the edits are:
@@ -34,5 +36,8 @@ n2LL <- function(x, cov_func, outer.W, y, X, W, mean.est = NULL, taper = NULL,
 #   pr <- .Call(C_vcb_predict, gpu, cov.par, mu, newlocs, newX, newW, q, compute.y.var)
 #     replaces the body of predict.SVC_mle (predict-SVC_mle.R:80-267): list(eff, y.pred, y.var)
 # SVC_selection: CD_mu's  R.t.inv <- solve(t(R)); X.tilde <- R.t.inv %*% X  (SVC_selection.R:30-35) becomes
-#   .Call(C_vcb_n2ll, gpu, theta.k, rep(0, p)); Z <- .Call(C_vcb_whitened, gpu, n, p)   # cbind(X.tilde, y.tilde)
-GLS_chol.matrix <- function(R, X, y) as.numeric(.Call(C_vcb_gls_chol, R, as.matrix(X), as.numeric(y), 0L))
+#   .Call(C_vcb_n2ll, gpu, theta.k, rep(0, p), p); Z <- .Call(C_vcb_whitened, gpu, n, p)   # cbind(X.tilde, y.tilde)
+GLS_chol.matrix <- function(R, X, y) {                  # p x 1 matrix, as utils.R:93-101 returns it
+  X <- as.matrix(X); storage.mode(X) <- "double"; storage.mode(R) <- "double"
+  .Call(C_vcb_gls_chol, R, X, as.numeric(y), 0L)
+}

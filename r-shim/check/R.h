@@ -20,6 +20,7 @@ int Rf_asLogical(SEXP);
 int Rf_nrows(SEXP);
 int Rf_ncols(SEXP);
 int Rf_length(SEXP);
+SEXP Rf_coerceVector(SEXP, unsigned int);
 int Rf_isNull(SEXP);
 SEXP Rf_allocVector(unsigned int, ptrdiff_t);
 SEXP Rf_allocMatrix(unsigned int, int, int);

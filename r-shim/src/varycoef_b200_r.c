@@ -40,6 +40,11 @@ SEXP vcb_create(SEXP locs, SEXP X, SEXP W, SEXP y, SEXP cov_id, SEXP dist_id, SE
   cfg.taper_id = Rf_asInteger(taper_id);
   cfg.taper_range = Rf_asReal(taper_range);
   cfg.device = Rf_asInteger(device);
+  /* integer coordinates / design columns (a 1:n grid, dummy variables) arrive as INTSXP: coerce, REAL() would fail */
+  locs = PROTECT(Rf_coerceVector(locs, REALSXP));
+  X = PROTECT(Rf_coerceVector(X, REALSXP));
+  W = PROTECT(Rf_coerceVector(W, REALSXP));
+  y = PROTECT(Rf_coerceVector(y, REALSXP));
   const int64_t n = Rf_nrows(X);
   vc_handle* h = NULL;
   int rc = vc_create(&h, &cfg, n, Rf_ncols(locs), Rf_ncols(X), Rf_ncols(W),
@@ -47,21 +52,23 @@ SEXP vcb_create(SEXP locs, SEXP X, SEXP W, SEXP y, SEXP cov_id, SEXP dist_id, SE
   if (rc != VC_OK) Rf_error("varycoef_b200 (%d): %s", rc, vc_last_error(NULL));
   SEXP ext = PROTECT(R_MakeExternalPtr(h, R_NilValue, R_NilValue));
   R_RegisterCFinalizerEx(ext, vcb_finalizer, TRUE);
-  UNPROTECT(1);
+  UNPROTECT(5);
   return ext;
 }
 
-/* .Call(C_vcb_n2ll, handle, theta, mu or NULL) -> numeric(1) with attributes mu, logdet, quad */
-SEXP vcb_n2ll(SEXP ext, SEXP theta, SEXP mu) {
+/* .Call(C_vcb_n2ll, handle, theta, mu or NULL, p) -> numeric(1) with attributes mu (length p), logdet, quad */
+SEXP vcb_n2ll(SEXP ext, SEXP theta, SEXP mu, SEXP p_) {
   vc_handle* h = vcb_get(ext);
   const int fixed = !Rf_isNull(mu);
+  const int p = Rf_asInteger(p_);
+  if (p < 1 || (fixed && Rf_length(mu) != p)) Rf_error("varycoef_b200: mu must have length p");
   double val, logdet, quad;
-  SEXP mu_out = PROTECT(Rf_allocVector(REALSXP, fixed ? Rf_length(mu) : 128));
+  SEXP mu_out = PROTECT(Rf_allocVector(REALSXP, p));
   int rc = vc_n2ll(h, REAL(theta), fixed ? VC_MU_FIXED : VC_MU_GLS, fixed ? REAL(mu) : NULL,
                    &val, REAL(mu_out), &logdet, &quad);
   vcb_check(rc, h);
   SEXP out = PROTECT(Rf_ScalarReal(val));
-  Rf_setAttrib(out, Rf_install("mu"), mu_out);       /* first p entries are the mean used (GLS estimate or mu) */
+  Rf_setAttrib(out, Rf_install("mu"), mu_out);       /* the mean used: GLS estimate or the caller's mu */
   Rf_setAttrib(out, Rf_install("logdet"), Rf_ScalarReal(logdet));
   Rf_setAttrib(out, Rf_install("quad"), Rf_ScalarReal(quad));
   UNPROTECT(2);
@@ -131,10 +138,11 @@ SEXP vcb_whitened(SEXP ext, SEXP n_, SEXP p_) {
   return Z;
 }
 
-/* .Call(C_vcb_gls_chol, R, X, y, device) -> mu: GLS_chol.matrix (R-pkg/R/utils.R:93-101) */
+/* .Call(C_vcb_gls_chol, R, X, y, device) -> mu as a p x 1 matrix, as GLS_chol.matrix returns it
+ * (R-pkg/R/utils.R:93-101; n2LL uses it in X %*% mu) */
 SEXP vcb_gls_chol(SEXP R, SEXP X, SEXP y, SEXP device) {
   const int p = Rf_ncols(X);
-  SEXP mu = PROTECT(Rf_allocVector(REALSXP, p));
+  SEXP mu = PROTECT(Rf_allocMatrix(REALSXP, p, 1));
   int rc = vc_gls_chol(Rf_asInteger(device), (int64_t) Rf_nrows(X), p, REAL(R), REAL(X), REAL(y), REAL(mu));
   if (rc == VC_ERR_INVALID) Rf_error("GLS_chol: R must be an upper Cholesky factor with a positive diagonal");
   if (rc != VC_OK) Rf_error("varycoef_b200 (%d): %s", rc, vc_last_error(NULL));
@@ -144,7 +152,7 @@ SEXP vcb_gls_chol(SEXP R, SEXP X, SEXP y, SEXP device) {
 
 static const R_CallMethodDef vcb_calls[] = {
   {"C_vcb_create", (DL_FUNC) &vcb_create, 10},
-  {"C_vcb_n2ll", (DL_FUNC) &vcb_n2ll, 3},
+  {"C_vcb_n2ll", (DL_FUNC) &vcb_n2ll, 4},
   {"C_vcb_n2ll_batch", (DL_FUNC) &vcb_n2ll_batch, 3},
   {"C_vcb_post", (DL_FUNC) &vcb_post, 4},
   {"C_vcb_predict", (DL_FUNC) &vcb_predict, 8},

@@ -205,6 +205,51 @@ def test_batch_equals_single_and_is_deterministic():
         assert np.array_equal(batch, obj.n2LL_batch(xs))
 
 
+@pytest.mark.parametrize("n,m,reps", [(1000, 17, 12), (2000, 17, 8), (5000, 13, 4), (10000, 9, 2)])
+def test_batch_equals_single_stress(n, m, reps):
+    """Evaluation lanes share the persistent update kernel, the streams and the events of the handle: a latent
+    race would show up as a batch value that differs from the one-at-a-time value.  Repeated, bit-exact."""
+    from varycoef_b200 import SVCObjective
+    locs, X, W, y = synth(n, 3, 100 + n, 2)
+    base = theta_for(3)
+    xs = np.vstack([base * (1 + 0.004 * k) for k in range(m)])
+    with SVCObjective(y, X, locs, profileLik=True) as obj:
+        single = np.array([obj.n2LL(x) for x in xs])
+        for _ in range(reps):
+            assert np.array_equal(single, obj.n2LL_batch(xs))
+        # and interleaved: a single evaluation between batches must not disturb the lanes
+        assert obj.n2LL(xs[3]) == single[3]
+        assert np.array_equal(single, obj.n2LL_batch(xs))
+
+
+@pytest.mark.parametrize("cov,n,dim", [("mat52", 2500, 2), ("mat32", 2500, 2), ("exp", 2500, 1), ("mat52", 1200, 1)])
+def test_parity_at_the_optimiser_default_bounds(cov, n, dim):
+    """The optimiser's default lower bound on the nugget is 1e-6 and its upper bound on the range is ten
+    times the median distance (R-pkg/R/utils.R:336-396).  There cond(L_jj) of a 128 x 128 diagonal tile is
+    large and the panel solve multiplies by the explicit tile inverse: -2logL must still agree with the
+    oracle's backward-stable LAPACK solves to 1e-10."""
+    from varycoef_b200 import SVCObjective
+    from varycoef_b200._lib import NotPositiveDefinite
+    o = _oracle()
+    locs, X, W, y = synth(n, 2, 300 + n, dim)
+    D = o.own_dist(locs)
+    med = float(np.median(D))
+    vy = float(np.var(y, ddof=1))
+    with SVCObjective(y, X, locs, cov_name=cov, profileLik=True) as obj:
+        for rng_mult, tau2 in [(10.0, 1e-6), (1.0, 1e-6), (10.0, 1e-3), (0.25, 1e-6)]:
+            theta = np.array([rng_mult * med, vy / 3, rng_mult * med * 0.7, vy / 3, tau2])
+            try:
+                ref = o.n2ll(theta, D, X, W, y, cov, profile=True, parts=True)
+            except np.linalg.LinAlgError:
+                # numerically singular in LAPACK too: the GPU path must report the same condition
+                with pytest.raises(NotPositiveDefinite):
+                    obj.n2LL(theta)
+                continue
+            got = obj.n2LL(theta, parts=True)
+            assert _rel(got["n2ll"], ref["n2ll"]) <= TOL_N2LL, (cov, rng_mult, tau2, got["n2ll"], ref["n2ll"])
+            assert _rel(got["logdet"], ref["logdet"]) <= 1e-9
+
+
 def test_properties_at_scale_permutation_scaling_and_third_path():
     """n = 12 000 (beyond what the faithful oracle finishes in seconds): invariances of the
     Gaussian likelihood plus an independent third path (torch/cuSOLVER Cholesky of the GPU-built
@@ -552,6 +597,34 @@ def test_config_c5_n20000_tapered_dense_on_gpu():
     ref = n * np.log(2 * np.pi) + logdet + float((rz @ rz).item())
     assert abs(r["n2ll"] - ref) <= TOL_N2LL * abs(ref)
     assert _rel(r["mu"], mu) <= 1e-9
+
+
+def test_config_c3_n50000_headline_against_cusolver_third_path():
+    """BASELINE config 3 at full size (n = 50 000, p = q = 3, exp): -2logL, log-det, quadratic form and mu-hat
+    of the hand-written path against an independent cuSOLVER/cuBLAS evaluation of the GPU-built Sigma_y
+    (tools/third_path.py), plus the y -> c y scaling law of the Gaussian likelihood.  ~60 GB of HBM."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from third_path import third_path_n2ll
+    import bench
+    from varycoef_b200 import SVCObjective
+    n, p, cov, _, seed_off, _ = bench.WORKLOADS["c3"]
+    locs, X, y, L = bench.make_inputs(n, p, seed_off)
+    theta = bench.theta_stencil(n, p, p, L, y)[0]
+    with SVCObjective(y, X, locs, cov_name=cov, profileLik=True) as obj:
+        r = obj.n2LL(theta, parts=True)
+        ref = third_path_n2ll(obj, theta, X, y)
+        assert _rel(r["n2ll"], ref["n2ll"]) <= TOL_N2LL, (r["n2ll"], ref["n2ll"])
+        assert _rel(r["logdet"], ref["logdet"]) <= TOL_N2LL
+        assert abs(r["quad"] - ref["quad"]) <= TOL_N2LL * abs(ref["n2ll"])
+        assert _rel(r["mu"], ref["mu"]) <= 1e-8
+        # scaling law: quad(c y) = c^2 quad(y), log-det unchanged, mu-hat scales with c
+        obj.set_data(y=3.0 * y)
+        r3 = obj.n2LL(theta, parts=True)
+        assert _rel(r3["quad"], 9.0 * r["quad"]) <= 1e-11 and r3["logdet"] == r["logdet"]
+        assert _rel(r3["mu"], 3.0 * r["mu"]) <= 1e-10
 
 
 def test_fallback_kernels_agree_with_default_path():

@@ -94,3 +94,5 @@ def test_selection_grid_runs_and_selects_minimum():
     with SVCObjective(y, X, locs, W, profileLik=False) as obj2:
         with pytest.raises(ValueError):
             sel.PMLE_CD((0.1, 0.1), mle, obj2)
+        with pytest.raises(ValueError, match="profileLik"):
+            sel.SVC_selection(obj2, mle, ctl)

@@ -200,8 +200,8 @@ def test_graft_entry_build_and_reference_arm_json():
     import __graft_entry__ as g
     g.build()
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
-                          "--warmup", "1", "--cpu-sample-n", "600"], cwd=ROOT, capture_output=True, text=True,
-                         timeout=300)
+                          "--warmup", "1", "--cpu-sample-n", "600", "--cpu-fit-n", "300,900", "--problem-n", "2500"],
+                         cwd=ROOT, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr[-500:]
     lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
     assert len(lines) == 1
@@ -210,19 +210,15 @@ def test_graft_entry_build_and_reference_arm_json():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["value"] > 0
     assert d["metric"].startswith("-2logL evals/sec")
-
-
-def test_split_schedule_model_has_no_unordered_conflicts():
-    """tools/schedule_model.py mirrors the host calls of the opt-in critical-first schedule (vc_chol.cu, panel_split):
-    every pair of kernels with conflicting tile accesses must be ordered by stream order or an event; dropping any of
-    the waits must be detected."""
-    sys.path.insert(0, os.path.join(ROOT, "tools"))
-    import schedule_model as sm
-    for nt, nb in [(5, 1), (6, 2), (7, 3)]:
-        for frac in (None, 0.5):
-            assert sm.factor_split(nt, nb, 1, frac, 2).check() == []
-    for drop in ("sq_ev_col", "sp_pending", "join", "ev_c0", "ev_t"):
-        assert sm.factor_split(7, 3, 1, 0.5, 1, drop).check() != [], drop
+    # ms_per_step is the measured time of one bounded step, not the extrapolated evaluation
+    assert d["ms_per_step"] < 60e3 and d["cpu_baseline"]["extrapolated"] is True
+    assert len(d["cpu_baseline"]["fit"]["samples"]) == 3
+    # the lean in-place sequence was really run at the full (here: overridden) n and agrees with the oracle port
+    lean = d["cpu_baseline"]["lean_measured"]
+    assert lean["n"] == 2500 and lean["seconds"] > 0 and np.isfinite(lean["n2ll"])
+    # same config keys as the GPU arm emits (bench.config_dict)
+    for k in ("workload", "n", "n_padded", "p", "q", "cov", "tapering", "mu_mode", "theta", "parallelism", "l2"):
+        assert k in d["config"], k
 
 
 def test_r_shim_type_checks_against_the_header():

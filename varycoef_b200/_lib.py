@@ -59,6 +59,7 @@ SIGNATURES = {
     "vc_n2ll": (C.c_int, [C.c_void_p, _dp, C.c_int32, _dp, _dp, _dp, _dp, _dp]),
     "vc_n2ll_batch": (C.c_int, [C.c_void_p, C.c_int32, _dp, C.c_int32, _dp, _dp, _dp, C.POINTER(C.c_int32)]),
     "vc_sigma": (C.c_int, [C.c_void_p, _dp, _dp]),
+    "vc_sigma_device": (C.c_int, [C.c_void_p, _dp, C.c_void_p]),
     "vc_get_chol": (C.c_int, [C.c_void_p, _dp]),
     "vc_get_whitened": (C.c_int, [C.c_void_p, _dp]),
     "vc_gls_chol": (C.c_int, [C.c_int32, C.c_int64, C.c_int32, _dp, _dp, _dp, _dp]),

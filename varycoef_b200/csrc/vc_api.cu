@@ -55,22 +55,13 @@ int vc_validate_cfg(const vc_config* cfg, int64_t n, int d, int p, int q, std::s
   return VC_OK;
 }
 
+static void free_lane(VcLane* L);
+
 void vc_free_handle(vc_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   if (h->dist) vc_dist_destroy(h);
-  for (VcLane* L : h->lanes) {
-    cudaFree(L->M.a); cudaFree(L->M.b); vc_chol_free_plans(L->cw);
-    cudaFree(L->cw.linv); cudaFree(L->cw.logdet_part); cudaFree(L->cw.info);
-    cudaFree(L->fw.gram_part); cudaFree(L->fw.quad_part); cudaFree(L->gram_dev);
-    if (L->cw.ev_panel) cudaEventDestroy(L->cw.ev_panel);
-    if (L->cw.ev_update) cudaEventDestroy(L->cw.ev_update);
-    if (L->cw.ev_col) cudaEventDestroy(L->cw.ev_col);
-    if (L->ev_done) cudaEventDestroy(L->ev_done);
-    if (L->st_main) cudaStreamDestroy(L->st_main);
-    if (L->st_panel) cudaStreamDestroy(L->st_panel);
-    delete L;
-  }
+  for (VcLane* L : h->lanes) free_lane(L);
   h->lanes.clear();
   if (h->ev_inputs) cudaEventDestroy(h->ev_inputs);
   cudaFree(h->M.a); cudaFree(h->M.b); vc_chol_free_plans(h->cw); cudaFree(h->locs); cudaFree(h->x); cudaFree(h->w); cudaFree(h->y);
@@ -245,36 +236,56 @@ static int lane_cap(const vc_handle* h) {
   return 1;
 }
 
-static VcLane* make_lane(vc_handle* h) {
+static void free_lane(VcLane* L) {
+  if (!L) return;
+  cudaFree(L->M.a); cudaFree(L->M.b); vc_chol_free_plans(L->cw);
+  cudaFree(L->cw.linv); cudaFree(L->cw.logdet_part); cudaFree(L->cw.info);
+  cudaFree(L->fw.gram_part); cudaFree(L->fw.quad_part); cudaFree(L->gram_dev);
+  if (L->cw.ev_panel) cudaEventDestroy(L->cw.ev_panel);
+  if (L->cw.ev_update) cudaEventDestroy(L->cw.ev_update);
+  if (L->cw.ev_col) cudaEventDestroy(L->cw.ev_col);
+  if (L->ev_done) cudaEventDestroy(L->ev_done);
+  if (L->st_main) cudaStreamDestroy(L->st_main);
+  if (L->st_panel) cudaStreamDestroy(L->st_panel);
+  delete L;
+}
+
+// A lane joins h->lanes only when every stream, event and buffer of it exists: a half-built lane must
+// never be visible to a later batch (it would launch on null pointers).  Throws VcError on failure.
+static void make_lane(vc_handle* h) {
   VcLane* L = new VcLane();
+  try {
+    const int64_t np = h->n_pad;
+    int lo = 0, hi = 0;
+    VC_CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    VC_CUDA_TRY(cudaStreamCreateWithPriority(&L->st_main, cudaStreamNonBlocking, lo));
+    VC_CUDA_TRY(cudaStreamCreateWithPriority(&L->st_panel, cudaStreamNonBlocking, hi));
+    VC_CUDA_TRY(cudaEventCreateWithFlags(&L->cw.ev_panel, cudaEventDisableTiming));
+    VC_CUDA_TRY(cudaEventCreateWithFlags(&L->cw.ev_update, cudaEventDisableTiming));
+    VC_CUDA_TRY(cudaEventCreateWithFlags(&L->cw.ev_col, cudaEventDisableTiming));
+    VC_CUDA_TRY(cudaEventCreateWithFlags(&L->ev_done, cudaEventDisableTiming));
+    L->M = h->M;
+    L->M.a = nullptr; L->M.b = nullptr;
+    L->M.nbt = 1; L->M.ldb = VC_BORDER_ROWS;
+    VC_CUDA_TRY(cudaMalloc(&L->M.a, (size_t)L->M.lda * np * sizeof(double)));
+    VC_CUDA_TRY(cudaMalloc(&L->M.b, (size_t)L->M.ldb * np * sizeof(double)));
+    L->cw.nb_tiles = h->cw.nb_tiles; L->cw.lookahead = h->cw.lookahead;
+    L->cw.legacy_syrk = h->cw.legacy_syrk; L->cw.legacy_potrf = h->cw.legacy_potrf; L->cw.num_sms = h->cw.num_sms;
+    L->cw.st_main = L->st_main; L->cw.st_panel = L->st_panel;
+    VC_CUDA_TRY(cudaMalloc(&L->cw.linv, (size_t)L->M.nt * VC_TILE * VC_TILE * sizeof(double)));
+    VC_CUDA_TRY(cudaMemsetAsync(L->cw.linv, 0, (size_t)L->M.nt * VC_TILE * VC_TILE * sizeof(double), L->st_main));
+    VC_CUDA_TRY(cudaMalloc(&L->cw.logdet_part, (size_t)L->M.nt * sizeof(double)));
+    VC_CUDA_TRY(cudaMalloc(&L->cw.info, sizeof(int)));
+    const int m = h->p + 1;
+    L->fw.blocks = h->fw.blocks;
+    VC_CUDA_TRY(cudaMalloc(&L->fw.gram_part, (size_t)L->fw.blocks * m * (m + 1) * sizeof(double)));
+    VC_CUDA_TRY(cudaMalloc(&L->fw.quad_part, (size_t)L->fw.blocks * 2 * sizeof(double)));
+    VC_CUDA_TRY(cudaMalloc(&L->gram_dev, (size_t)m * m * sizeof(double)));
+  } catch (...) {
+    free_lane(L);
+    throw;
+  }
   h->lanes.push_back(L);
-  const int64_t np = h->n_pad;
-  int lo = 0, hi = 0;
-  VC_CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-  VC_CUDA_TRY(cudaStreamCreateWithPriority(&L->st_main, cudaStreamNonBlocking, lo));
-  VC_CUDA_TRY(cudaStreamCreateWithPriority(&L->st_panel, cudaStreamNonBlocking, hi));
-  VC_CUDA_TRY(cudaEventCreateWithFlags(&L->cw.ev_panel, cudaEventDisableTiming));
-  VC_CUDA_TRY(cudaEventCreateWithFlags(&L->cw.ev_update, cudaEventDisableTiming));
-  VC_CUDA_TRY(cudaEventCreateWithFlags(&L->cw.ev_col, cudaEventDisableTiming));
-  VC_CUDA_TRY(cudaEventCreateWithFlags(&L->ev_done, cudaEventDisableTiming));
-  L->M = h->M;
-  L->M.a = nullptr; L->M.b = nullptr;
-  L->M.nbt = 1; L->M.ldb = VC_BORDER_ROWS;
-  VC_CUDA_TRY(cudaMalloc(&L->M.a, (size_t)L->M.lda * np * sizeof(double)));
-  VC_CUDA_TRY(cudaMalloc(&L->M.b, (size_t)L->M.ldb * np * sizeof(double)));
-  L->cw.nb_tiles = h->cw.nb_tiles; L->cw.lookahead = h->cw.lookahead;
-  L->cw.legacy_syrk = h->cw.legacy_syrk; L->cw.legacy_potrf = h->cw.legacy_potrf; L->cw.num_sms = h->cw.num_sms;
-  L->cw.st_main = L->st_main; L->cw.st_panel = L->st_panel;
-  VC_CUDA_TRY(cudaMalloc(&L->cw.linv, (size_t)L->M.nt * VC_TILE * VC_TILE * sizeof(double)));
-  VC_CUDA_TRY(cudaMemsetAsync(L->cw.linv, 0, (size_t)L->M.nt * VC_TILE * VC_TILE * sizeof(double), L->st_main));
-  VC_CUDA_TRY(cudaMalloc(&L->cw.logdet_part, (size_t)L->M.nt * sizeof(double)));
-  VC_CUDA_TRY(cudaMalloc(&L->cw.info, sizeof(int)));
-  const int m = h->p + 1;
-  L->fw.blocks = h->fw.blocks;
-  VC_CUDA_TRY(cudaMalloc(&L->fw.gram_part, (size_t)L->fw.blocks * m * (m + 1) * sizeof(double)));
-  VC_CUDA_TRY(cudaMalloc(&L->fw.quad_part, (size_t)L->fw.blocks * 2 * sizeof(double)));
-  VC_CUDA_TRY(cudaMalloc(&L->gram_dev, (size_t)m * m * sizeof(double)));
-  return L;
 }
 
 // enqueue one evaluation on a lane (lane < 0: the handle's own matrix and streams); result record
@@ -336,8 +347,16 @@ extern "C" int vc_n2ll_batch(vc_handle* h, int32_t m, const double* thetas, int3
                                     h->p * sizeof(double), m, cudaMemcpyHostToDevice, h->st_main));
     // lanes: evaluation e runs on lane (m - 1 - e) % nl, so the LAST one lands on the handle's own
     // matrix (vc_get_chol / vc_get_whitened / vc_post refer to it)
-    const int nl = std::min(m, lane_cap(h));
-    while ((int)h->lanes.size() < nl - 1) make_lane(h);
+    int nl = std::min(m, lane_cap(h));
+    while ((int)h->lanes.size() < nl - 1) {
+      try {
+        make_lane(h);
+      } catch (const VcError& e) {
+        if (e.code != VC_ERR_OOM) throw;
+        (void)cudaGetLastError();                 // out of device memory: run the batch on the lanes that exist
+        nl = (int)h->lanes.size() + 1;
+      }
+    }
     if (nl > 1) {
       if (!h->ev_inputs) VC_CUDA_TRY(cudaEventCreateWithFlags(&h->ev_inputs, cudaEventDisableTiming));
       VC_CUDA_TRY(cudaEventRecord(h->ev_inputs, h->st_main));   // inputs / mu staged on st_main
@@ -427,6 +446,25 @@ extern "C" int vc_sigma(vc_handle* h, const double* theta, double* out) {
     cudaFree(dev);
   } catch (const VcError& e) {
     cudaFree(dev);
+    return vc_fail(h, e.code, e.msg);
+  }
+  return VC_OK;
+}
+
+extern "C" int vc_sigma_device(vc_handle* h, const double* theta, double* out_dev) {
+  if (!h || !theta || !out_dev) return VC_ERR_INVALID;
+  if (h->dist) return vc_fail(h, VC_ERR_INVALID, "vc_sigma_device is not available on a distributed handle");
+  VcTheta th;
+  if (vc_make_theta(h, theta, &th) != VC_OK) return vc_fail(h, VC_ERR_INVALID, "invalid theta");
+  try {
+    VC_CUDA_TRY(cudaSetDevice(h->device));
+    cudaPointerAttributes attr;
+    VC_CUDA_TRY(cudaPointerGetAttributes(&attr, out_dev));
+    if (attr.type != cudaMemoryTypeDevice || attr.device != h->device)
+      return vc_fail(h, VC_ERR_INVALID, "out_dev must be device memory of the handle's GPU");
+    vc_launch_sigma_full(out_dev, h->n, h->n_pad, th, h->d, h->locs, h->w, h->st_main, &h->launches);
+    VC_CUDA_TRY(cudaStreamSynchronize(h->st_main));
+  } catch (const VcError& e) {
     return vc_fail(h, e.code, e.msg);
   }
   return VC_OK;

@@ -243,11 +243,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_syrk_tiles(GemmArgs p) {
     }
 }
 
-// ---- 32-row strips of ONE tile: the tiles on the critical path --------------------------------
-// The chain potrf(j) -> TRSM of row tile j+1 -> update of tile (j+1, j+1) -> potrf(j+1) bounds a
-// factorisation at n <= 10 000.  A whole 128x128x128 product costs 16.7 us on one SM whatever the
-// kernel; cut into four 32-row strips on four SMs it costs a quarter.  Same per-element DMMA order as
-// the full-tile kernels, so results are bit-identical.  Block b: tile b / 4, strip b % 4.
+// ---- 32-row strips of a tile: remainder waves of the persistent update ------------------------
+// A whole 128x128xK product occupies one SM for its full duration whatever the kernel; cut into
+// four 32-row strips on four SMs it takes a quarter.  Same per-element DMMA order as the full-tile
+// kernels, so results are bit-identical.  Block b: tile b / 4, strip b % 4.
 constexpr int STRIP = 32;
 __device__ __forceinline__ void warp_stage_strip(const double* sa, const double* sb, int tig, double (&acc)[4][2][2]) {
 #pragma unroll
@@ -303,7 +302,6 @@ __device__ __forceinline__ void strip_mainloop(const double* __restrict__ Ag, in
   cp_async_wait<0>();
   __syncthreads();
 }
-template <bool TRSM>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) k_strip(GemmArgs p) {
   extern __shared__ __align__(16) double smem[];
   const int t = blockIdx.x >> 2, s = blockIdx.x & 3;
@@ -314,42 +312,23 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_strip(GemmArgs p) {
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 2; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-  if (TRSM) {   // main row tile jt + 1 + i_skip + t:  X = A * Linv^T, in place (a strip reads only its own rows)
-    int64_t ld;
-    double* Ct = c_tile_ptr(p, p.jt + 1 + p.i_skip + t, p.jt, ld) + STRIP * s;
-    strip_mainloop(Ct, ld, p.linv, TILE, TILE, acc, smem);
-    double* cbase = Ct + g + (int64_t)(warp * 16 + 2 * tig) * ld;
+  // C(I, J) -= P_I P_J^T on rows [32 s, 32 s + 32) of the tile
+  const int packed = p.tiles[t];
+  const int I = packed & 0xffff, J = packed >> 16;
+  int64_t ldc, ldpi, ldpj;
+  double* Ct = c_tile_ptr(p, I, J, ldc) + STRIP * s;
+  const double* Pi = op_ptr(p, p.src_a, I, 0, ldpi) + STRIP * s;
+  const double* Pj = op_ptr(p, p.src_b, J, 0, ldpj);
+  strip_mainloop(Pi, ldpi, Pj, ldpj, p.K, acc, smem);
+  double* cbase = Ct + g + (int64_t)(warp * 16 + 2 * tig) * ldc;
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        double* c = cbase + i * 8 + (int64_t)(j * 8) * ld;
-        c[0] = acc[i][j][0];
-        c[ld] = acc[i][j][1];
-      }
-  } else {      // C(I, J) -= P_I P_J^T
-    const int packed = p.tiles[t];
-    const int I = packed & 0xffff, J = packed >> 16;
-    int64_t ldc, ldpi, ldpj;
-    double* Ct = c_tile_ptr(p, I, J, ldc) + STRIP * s;
-    const double* Pi = op_ptr(p, p.src_a, I, 0, ldpi) + STRIP * s;
-    const double* Pj = op_ptr(p, p.src_b, J, 0, ldpj);
-    strip_mainloop(Pi, ldpi, Pj, ldpj, p.K, acc, smem);
-    double* cbase = Ct + g + (int64_t)(warp * 16 + 2 * tig) * ldc;
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        double* c = cbase + i * 8 + (int64_t)(j * 8) * ldc;
-        if (p.n_main == 1) {   // exclusive owner of the tile (critical-first schedule): load + store, same rounding
-          __stcg(c, __ldcg(c) + (-acc[i][j][0]));
-          __stcg(c + ldc, __ldcg(c + ldc) + (-acc[i][j][1]));
-        } else {
-          red_add_f64(c, -acc[i][j][0]);
-          red_add_f64(c + ldc, -acc[i][j][1]);
-        }
-      }
-  }
+    for (int j = 0; j < 2; ++j) {
+      double* c = cbase + i * 8 + (int64_t)(j * 8) * ldc;
+      red_add_f64(c, -acc[i][j][0]);
+      red_add_f64(c + ldc, -acc[i][j][1]);
+    }
 }
 
 // ---- update, persistent + warp-specialised ----------------------------------------------------
@@ -1269,8 +1248,7 @@ void vc_chol_init() {
   if (done) return;
   VC_CUDA_TRY(cudaFuncSetAttribute(k_trsm_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
   VC_CUDA_TRY(cudaFuncSetAttribute(k_syrk_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
-  VC_CUDA_TRY(cudaFuncSetAttribute(k_strip<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
-  VC_CUDA_TRY(cudaFuncSetAttribute(k_strip<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+  VC_CUDA_TRY(cudaFuncSetAttribute(k_strip, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
   VC_CUDA_TRY(cudaFuncSetAttribute(k_syrk_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM));
   VC_CUDA_TRY(cudaFuncSetAttribute(k_potrf128, cudaFuncAttributeMaxDynamicSharedMemorySize, POTRF_SMEM));
   VC_CUDA_TRY(cudaFuncSetAttribute(k_potrf128b<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, POTRFB_SMEM));
@@ -1298,8 +1276,6 @@ void vc_chol_invert_diag_tiles(const VcMatrix& M, VcCholWork& w, int64_t* launch
 }
 
 void vc_chol_free_plans(VcCholWork& w) {
-  for (auto& e : w.ev_aux) { if (e) cudaEventDestroy(e); e = nullptr; }
-  if (w.st_aux) { cudaStreamDestroy(w.st_aux); w.st_aux = nullptr; }
   if (w.plan_factor.tiles_dev) cudaFree(w.plan_factor.tiles_dev);
   if (w.plan_solve.tiles_dev) cudaFree(w.plan_solve.tiles_dev);
   w.plan_factor = VcCholPlan();
@@ -1393,7 +1369,7 @@ void vc_launch_syrk(const VcGemmArgs& g, int num_sms, bool legacy, cudaStream_t 
     t.tiles = g.tiles + m.ntiles;
     t.ntiles = tail;
     TraceScope ts("utail", st, tail, 4 * tail);
-    k_strip<false><<<4 * tail, GEMM_THREADS, GEMM_SMEM, st>>>(t);
+    k_strip<<<4 * tail, GEMM_THREADS, GEMM_SMEM, st>>>(t);
     ++*launches;
   }
 }
@@ -1506,113 +1482,20 @@ void vc_chol_factor(const VcMatrix& M, VcCholWork& w, int64_t* launches, int mod
     trace_dump(nt, nb);
     return;
   }
-  // Critical-first scheduling (default; VC_NO_STRIPS=1 restores the plain panel order): the tiles on the
-  // chain potrf(j) -> TRSM(row tile j+1) -> update(tile (j+1, j+1)) -> potrf(j+1) are computed in four
-  // 32-row strips on sp, everything else of the panel (other row tiles, rest of the inner update) runs
-  // on a third stream sq and only has to be back before the next TRSM.
-  static const bool no_strips = getenv("VC_NO_STRIPS") != nullptr;
-  // measured: pays up to n ~ 6000 (the chain bounds the evaluation); beyond, the trailing update does and
-  // the extra launches / reserved SMs cost 1-2 %
-  // OPT-IN (VC_SPLIT_SCHED=1): single evaluations gain 6-15 % at n <= 5000, but multi-lane batches
-  // (vc_n2ll_batch) have produced wrong factors with it -- not yet understood, so it is off by default
-  static const bool split_sched = getenv("VC_SPLIT_SCHED") != nullptr;
-  const bool split = split_sched && !w.legacy_syrk && !no_strips && nt <= 48;
-  cudaStream_t sq = sp;
-  cudaEvent_t ev_p = nullptr, ev_t = nullptr, ev_u = nullptr, ev_q = nullptr, ev_c0 = nullptr;
-  if (split) {
-    if (!w.st_aux) {
-      VC_CUDA_TRY(cudaStreamCreateWithFlags(&w.st_aux, cudaStreamNonBlocking));
-      for (auto& e : w.ev_aux) VC_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    }
-    sq = w.st_aux;
-    ev_p = w.ev_aux[0]; ev_t = w.ev_aux[1]; ev_u = w.ev_aux[2]; ev_q = w.ev_aux[3]; ev_c0 = w.ev_aux[4];
-  }
-  auto strip_update = [&](size_t call, cudaStream_t st) {       // first tile of a plan call, in strips
-    const VcUpdateCall& c = pl.calls[call];
-    GemmArgs g = base_args(M);
-    g.k0 = c.k0; g.K = c.K; g.tiles = pl.tiles_dev + c.tile_off; g.ntiles = 1;
-    static const bool ldst = getenv("VC_SPLIT_LDST") != nullptr;                  // diagnostics: no RED on this tile
-    g.n_main = ldst ? 1 : 0;
-    static const bool no_ustrip = getenv("VC_SPLIT_NO_USTRIP") != nullptr;       // diagnostics
-    if (no_ustrip) {
-      vc_launch_syrk(g, 1, false, st, launches);
-      return;
-    }
-    TraceScope ts("ustrip", st, 1, 4);
-    k_strip<false><<<4, GEMM_THREADS, GEMM_SMEM, st>>>(g);
-    ++*launches;
-  };
-  // wait_ev: the columns of this block have received every earlier update (nullptr for the first block)
-  auto panel_split = [&](int ob, cudaEvent_t wait_ev) {
-    const int oe = std::min(ob + nb, nt);
-    size_t call = first_call[ob / nb];
-    cudaEvent_t pending = wait_ev;
-    if (wait_ev) VC_CUDA_TRY(cudaStreamWaitEvent(sq, wait_ev, 0));
-    for (int jt = ob; jt < oe; ++jt) {
-      double* diag = M.a + (int64_t)jt * TILE * (M.lda + 1);
-      vc_launch_potrf(diag, M.lda, jt, w.linv, w.logdet_part, w.info, w.legacy_potrf, sp, launches);
-      VC_CUDA_TRY(cudaEventRecord(ev_p, sp));
-      VC_CUDA_TRY(cudaStreamWaitEvent(sq, ev_p, 0));
-      if (pending) {
-        VC_CUDA_TRY(cudaStreamWaitEvent(sp, pending, 0));
-        pending = nullptr;
-      }
-      GemmArgs g = base_args(M);
-      g.linv = w.linv + (int64_t)jt * TILE * TILE;
-      g.k0 = jt * TILE; g.K = TILE; g.jt = jt;
-      const int n_main = nt - (jt + 1);
-      if (n_main > 0) {                                          // row tile jt+1, four strips, on sp
-        static const bool no_tstrip = getenv("VC_SPLIT_NO_TSTRIP") != nullptr;   // diagnostics
-        if (no_tstrip) {
-          GemmArgs g1 = g;
-          g1.n_main = 1;
-          vc_launch_trsm(g1, 1, sp, launches);
-        } else {
-          TraceScope ts("tstrip", sp, jt, 4);
-          k_strip<true><<<4, GEMM_THREADS, GEMM_SMEM, sp>>>(g);
-          ++*launches;
-        }
-      }
-      g.i_skip = 1;                                              // the other row tiles + border, on sq
-      g.n_main = std::max(n_main - 1, 0);
-      vc_launch_trsm(g, g.n_main + nbt, sq, launches);
-      const VcUpdateCall& c = pl.calls[call];
-      if (c.ntiles > 0) {                                        // inner update: tile (jt+1, jt+1) first
-        strip_update(call, sp);
-        VC_CUDA_TRY(cudaEventRecord(ev_t, sp));
-        VC_CUDA_TRY(cudaStreamWaitEvent(sq, ev_t, 0));
-        launch_update(M, w, pl, call, sq, launches, 0, 1, c.ntiles - 1);
-        VC_CUDA_TRY(cudaEventRecord(ev_u, sq));
-        pending = ev_u;
-      }
-      ++call;
-    }
-    VC_CUDA_TRY(cudaEventRecord(ev_q, sq));                      // the panel is complete when both streams are
-    VC_CUDA_TRY(cudaStreamWaitEvent(sp, ev_q, 0));
-  };
   // Lookahead, software-pipelined over the outer blocks:
   //   sm:  col(s) | rest A(s) on num_sms - R CTAs ............ | rest B(s) on every SM | col(s+1) ...
   //   sp:          panel(s+1): potrf / TRSM / inner updates ---^ (rest B and col(s+1) wait for it)
   // The next panel only touches columns [oe, ne), which the rest update neither reads nor writes.
-  if (split) panel_split(0, nullptr); else panel(0);
+  panel(0);
   VC_CUDA_TRY(cudaEventRecord(w.ev_panel, sp));
   for (int ob = 0; ob < nt; ob += nb) {
     const int oe = std::min(ob + nb, nt);
     if (oe >= nt) break;
     const size_t c_col = first_call[ob / nb] + (size_t)(oe - ob), c_rest = c_col + 1;
     VC_CUDA_TRY(cudaStreamWaitEvent(sm, w.ev_panel, 0));
-    if (split) {
-      // column update: the next diagonal tile first (strips), so that its potrf starts at once
-      strip_update(c_col, sm);
-      VC_CUDA_TRY(cudaEventRecord(ev_c0, sm));
-      VC_CUDA_TRY(cudaStreamWaitEvent(sp, ev_c0, 0));
-      // leave a few SMs free: potrf(oe) and the TRSM strips must not queue behind a full-machine grid
-      launch_update(M, w, pl, c_col, sm, launches, 5, 1, pl.calls[c_col].ntiles - 1);
-    } else {
-      launch_update(M, w, pl, c_col, sm, launches);
-    }
+    launch_update(M, w, pl, c_col, sm, launches);
     VC_CUDA_TRY(cudaEventRecord(w.ev_col, sm));
-    if (!split) VC_CUDA_TRY(cudaStreamWaitEvent(sp, w.ev_col, 0));
+    VC_CUDA_TRY(cudaStreamWaitEvent(sp, w.ev_col, 0));
     const int rest_tiles = pl.calls[c_rest].ntiles;
     int nA = rest_tiles;
     int reserve = w.legacy_syrk ? 0 : vc_pick_reserved_sms(w.num_sms, nt + nbt - oe, nb, rest_tiles, &nA);
@@ -1623,7 +1506,7 @@ void vc_chol_factor(const VcMatrix& M, VcCholWork& w, int64_t* launches, int mod
       if (nosplit) nA = rest_tiles;
     }
     launch_update(M, w, pl, c_rest, sm, launches, reserve, 0, nA);
-    if (split) panel_split(oe, w.ev_col); else panel(oe);
+    panel(oe);
     VC_CUDA_TRY(cudaEventRecord(w.ev_panel, sp));
     if (nA < rest_tiles) {
       VC_CUDA_TRY(cudaStreamWaitEvent(sm, w.ev_panel, 0));

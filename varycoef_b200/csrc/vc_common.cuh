@@ -128,9 +128,6 @@ struct VcCholWork {
   cudaStream_t st_main, st_panel;
   cudaEvent_t ev_panel, ev_update, ev_col;
   VcCholPlan plan_factor, plan_solve;
-  // critical-first scheduling (created on first use, released by vc_chol_free_plans)
-  cudaStream_t st_aux = nullptr;
-  cudaEvent_t ev_aux[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 enum { VC_SWEEP_FACTOR = 0,   // potrf + TRSM + updates on every row tile (main + border)
        VC_SWEEP_SOLVE = 1,    // factor already resident: only the border rows are swept

@@ -199,6 +199,11 @@ class SVCObjective:
         check(lib().vc_sigma(self._h, ptr(theta), ptr(out)), self._h)
         return out
 
+    def Sigma_y_device(self, x, out_ptr):
+        """Sigma_y written to device memory (n x n column-major doubles at the raw pointer out_ptr)."""
+        theta = np.ascontiguousarray(np.asarray(x, dtype=np.float64).ravel()[:2 * self.q + 1])
+        check(lib().vc_sigma_device(self._h, ptr(theta), C.c_void_p(int(out_ptr))), self._h)
+
     def chol(self):
         """Upper factor R (R'R = Sigma_y) of the last evaluation -- base::chol's convention."""
         out = np.empty((self.n, self.n), order="F")

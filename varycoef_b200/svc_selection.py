@@ -207,6 +207,14 @@ def SVC_selection(obj_fun, mle_par, control=None):
     mle_par = np.asarray(mle_par, dtype=np.float64).ravel() if np.ndim(mle_par) else np.asarray([mle_par], float)
     if mle_par.size != 2 * q + 1 or not np.issubdtype(mle_par.dtype, np.number):
         raise ValueError("The mle.par argument must be a numeric vector of length %d!" % (2 * q + 1))
+    if not obj_fun.profileLik:
+        # The reference's CD_theta sets args$mean.est and calls n2LL with args$profile (SVC_selection.R:71-76):
+        # with profileLik = FALSE n2LL ignores mean.est and reads mu from x[2q+1 + 1:p] (objective_functions.R:31-43),
+        # which is NA for the length-(2q+1) x of the coordinate descent -- optim then stops with
+        # "L-BFGS-B needs finite values of 'fn'".  Same outcome here, with the cause spelled out.
+        raise ValueError("SVC_selection needs an objective extracted with profileLik = TRUE "
+                         "(SVC_mle_control(profileLik = TRUE, extract_fun = TRUE)): the coordinate descent "
+                         "fixes the mean through mean.est, which a non-profile n2LL ignores")
     if obj_fun.tapering is not None:
         raise NotImplementedError("SVC_selection on a tapered objective: the reference's CD_mu drops the "
                                   "taper (SVC_selection.R:30); not mirrored")
