@@ -49,5 +49,7 @@ if rank == 0 and single:
     print("single n2ll=%.12g  rel diff=%.3e  mu rel diff=%.3e  fixed-mu rel diff=%.3e" % (
         r1["n2ll"], abs(r1["n2ll"] - res["n2ll"]) / abs(r1["n2ll"]),
         np.max(np.abs(r1["mu"] - res["mu"]) / np.abs(r1["mu"])), abs(w2 - v2) / abs(w2)), flush=True)
+    bad = max(abs(r1["n2ll"] - res["n2ll"]) / abs(r1["n2ll"]), abs(w2 - v2) / abs(w2)) > 1e-13
+    print("DIST_CHECK " + ("FAIL" if bad else "OK"), flush=True)
 dist.barrier()
 dist.destroy_process_group()
