@@ -241,8 +241,9 @@ def extrapolate(samples, n):
                                "samples": [{"n": s[0], "build_s": s[1], "cubic_s": s[2]} for s in samples]}
 
 
-def lean_full(n, p, cov, seed_off, threads):
-    """The lean in-place sequence measured at the full n (needs 8 n^2 bytes of host RAM)."""
+def full_size_cpu(n, p, cov, seed_off, threads, with_dgesv):
+    """Measured at the FULL n on the host cores (needs 8 n^2 bytes of RAM, twice that with_dgesv):
+    the lean in-place sequence, and -- with_dgesv -- one of the reference's three dgesv calls on t(R)."""
     from oracle.lean_inplace import n2ll_lean_inplace
     try:
         import psutil
@@ -252,31 +253,43 @@ def lean_full(n, p, cov, seed_off, threads):
     need = 8.0 * n * n * 1.15 + 4e9
     if avail < need:
         return {"skipped": "host RAM available %.0f GB < %.0f GB needed" % (avail / 1e9, need / 1e9)}
+    with_dgesv = with_dgesv and avail >= 2 * need
     locs, X, y, L = make_inputs(n, p, seed_off)
     th = theta_stencil(n, p, p, L, y)[0]
     t0 = time.perf_counter()
-    r = n2ll_lean_inplace(th, locs, X, X, y, cov, threads=threads)
-    wall = time.perf_counter() - t0
-    return {"n": n, "seconds": wall, "evals_per_s": 1.0 / wall, "build_s": r["t_build"], "dpotrf_s": r["t_chol"],
-            "solve_s": r["t_solve"], "dpotrf_gflops": n ** 3 / 3.0 / r["t_chol"] / 1e9, "n2ll": r["n2ll"],
-            "logdet": r["logdet"], "mu": [float(v) for v in r["mu"]], "theta": [float(v) for v in th],
-            "sequence": "blocked in-place build (lower) -> dpotrf -> dtrtrs -> sum log diag; numpy/OpenBLAS, %d threads" % threads}
+    r = n2ll_lean_inplace(th, locs, X, X, y, cov, threads=threads, time_dgesv=with_dgesv)
+    wall = r["t_build"] + r["t_chol"] + r["t_solve"]
+    out = {"n": n, "seconds": wall, "evals_per_s": 1.0 / wall, "build_s": r["t_build"], "dpotrf_s": r["t_chol"],
+           "solve_s": r["t_solve"], "dpotrf_gflops": n ** 3 / 3.0 / r["t_chol"] / 1e9, "n2ll": r["n2ll"],
+           "logdet": r["logdet"], "mu": [float(v) for v in r["mu"]], "theta": [float(v) for v in th],
+           "sequence": "blocked in-place build (lower) -> dpotrf -> dtrtrs -> sum log diag; numpy/OpenBLAS, %d threads" % threads}
+    if "t_dgesv" in r:
+        out["dgesv_s"] = r["t_dgesv"]
+        out["dgesv_gflops"] = 2.0 * n ** 3 / 3.0 / r["t_dgesv"] / 1e9
+        out["dgesv_check"] = r["dgesv_check"]
+    out["wall_s"] = time.perf_counter() - t0
+    return out
 
 
-def cpu_arm_bounded(n, p, cov, seed_off, sizes):
-    """cpu_baseline of the GPU arm: ~10-30 s of CPU work -- the faithful sequence at two bounded sizes,
-    exponent fitted, extrapolated to n."""
-    samples = []
-    for n_s in sizes:
-        b, c, _, _ = cpu_eval_timed(n_s, p, cov, seed_off, faithful=True)
-        samples.append((n_s, b, c))
-    t_full, fit = extrapolate(samples, n)
-    return {"value": 1.0 / t_full, "unit": UNIT, "cores": blas_threads(), "kind": "port", "extrapolated": True,
-            "sample": ("faithful R op sequence (Sigma_y loop, dpotrf, 3x dgesv on the triangular factor, log-det) measured "
-                       "at n_s = %s, p=q=%d, %s; build x (n/n_s)^2, cubic part x (n/n_s)^%.2f (fitted %.2f) -> n=%d; host "
-                       "has %d usable cores" % ("/".join(str(s) for s in sizes), p, cov, fit["exponent_used"],
-                                                fit["fitted_exponent"], n, _host_threads())),
-            "sample_seconds": float(sum(s[1] + s[2] for s in samples)), "fit": fit}
+def cpu_baseline_gpu_arm(n, p, cov, seed_off, threads):
+    """cpu_baseline of the GPU arm (~10-40 s of CPU work): the lean in-place sequence -- the cheapest correct CPU
+    evaluation, NOT what R executes -- measured at the full n when host RAM allows; else the faithful sequence
+    at a bounded size, scaled with n^3."""
+    full = full_size_cpu(n, p, cov, seed_off, threads, with_dgesv=False)
+    if "skipped" not in full:
+        return {"value": full["evals_per_s"], "unit": UNIT, "cores": threads, "kind": "port", "extrapolated": False,
+                "sample": ("ONE full evaluation at n=%d, p=q=%d, %s with the LEAN in-place CPU sequence (blocked build of the "
+                           "lower triangle, dpotrf, dtrtrs, sum log diag; oracle/lean_inplace.py): %.1f s = build %.1f + dpotrf "
+                           "%.1f (%.0f GFLOP/s) + solves %.1f, %d BLAS threads.  The op sequence R actually executes (3 dgesv on "
+                           "the triangular factor, (q+2) n x n temporaries) costs ~9x the flops: `bench.py --impl reference`"
+                           % (n, p, cov, full["seconds"], full["build_s"], full["dpotrf_s"], full["dpotrf_gflops"],
+                              full["solve_s"], threads)),
+                "sample_seconds": full["seconds"], "n2ll": full["n2ll"], "theta": full["theta"], "detail": full}
+    b, c, _, _ = cpu_eval_timed(8000, p, cov, seed_off, faithful=True)
+    t_full, fit = extrapolate([(8000, b, c)], n)
+    return {"value": 1.0 / t_full, "unit": UNIT, "cores": threads, "kind": "port", "extrapolated": True,
+            "sample": "faithful R op sequence at n_s=8000 scaled with n^2 (build) and n^3 (cubic part); " + full["skipped"],
+            "sample_seconds": b + c, "fit": fit}
 
 
 def run_reference(args):
@@ -304,29 +317,43 @@ def run_reference(args):
             b, c, _, _ = cpu_eval_timed(n_f, p, cov, seed_off, faithful=True)
             samples.append((n_f, b, c))
             log("reference: faithful sample n=%d build %.2fs cubic %.2fs" % (n_f, b, c))
-    t_full, fit = extrapolate(samples, n)
-    lean = None
+    t_extrap, fit = extrapolate(samples, n)
+    n_l, tb_l, tc_l = max(samples)
+    build_full = tb_l * (n / n_l) ** 2            # the O(n^2) numpy passes of the faithful Sigma_y loop
+    full = None
     if not args.no_lean_full:
         try:
-            lean = lean_full(n, p, cov, seed_off, threads)
-            log("reference: lean at full n:", json.dumps(lean)[:300])
+            full = full_size_cpu(n, p, cov, seed_off, threads, with_dgesv=True)
+            log("reference: measured at full n:", json.dumps(full)[:400])
         except Exception as e:  # noqa: BLE001
-            lean = {"skipped": "failed: %r" % (e,)}
-    arm = {"value": 1.0 / t_full, "unit": UNIT, "cores": threads, "kind": "port", "extrapolated": True,
-           "sample": ("each step = one faithful evaluation (Sigma_y loop, dpotrf, 3x dgesv on the triangular factor, "
-                      "log-det; R-pkg/R/objective_functions.R:4-62) at n_s=%d, p=q=%d, %s, %d BLAS threads: median build "
-                      "%.3fs + cubic part %.3fs.  value = 1 / (build x (n/n_l)^2 + cubic x (n/n_l)^%.2f) from the largest "
-                      "sample n_l=%d; exponent = log-log slope of the two largest of n_s in %s (fitted %.3f).  The faithful sequence cannot run at "
-                      "n=%d (needs (q+5) 8 n^2 B = %.0f GB)" % (
-                          n_s, p, cov, threads, samples[0][1], samples[0][2], fit["exponent_used"],
-                          max(s[0] for s in samples), sorted(s[0] for s in samples), fit["fitted_exponent"], n,
-                          (p + 5) * 8.0 * n * n / 1e9)),
-           "sample_seconds": float(np.mean(step_s)), "fit": fit, "lean_measured": lean}
+            full = {"skipped": "failed: %r" % (e,)}
+    if full and "dgesv_s" in full:
+        # cubic part of the faithful sequence MEASURED at the full n: dpotrf + 3 x dgesv(t(R), .) (one of the three
+        # identical factorisations timed); only the O(n^2) build is scaled from the largest faithful sample
+        t_full = build_full + full["dpotrf_s"] + 3.0 * full["dgesv_s"]
+        how = ("cubic part MEASURED at n=%d: dpotrf %.1f s + 3 x dgesv on t(R) %.1f s (one of the three identical LU "
+               "factorisations timed, %.0f GFLOP/s); Sigma_y build %.1f s scaled x (n/n_l)^2 from the faithful sample at "
+               "n_l=%d" % (n, full["dpotrf_s"], full["dgesv_s"], full["dgesv_gflops"], build_full, n_l))
+        extrapolated = "build part only (O(n^2)); the O(n^3) part is measured at the full n"
+    else:
+        t_full = t_extrap
+        how = ("extrapolated from the largest faithful sample n_l=%d: build x (n/n_l)^2, cubic part x (n/n_l)^%.2f "
+               "(log-log slope of the two largest samples %.3f, clamped to [2, 3])" % (n_l, fit["exponent_used"],
+                                                                                      fit["fitted_exponent"]))
+        extrapolated = True
+    arm = {"value": 1.0 / t_full, "unit": UNIT, "cores": threads, "kind": "port", "extrapolated": extrapolated,
+           "sample": ("the op sequence R executes (Sigma_y loop, dpotrf, 3 x dgesv on the triangular factor, log-det; "
+                      "R-pkg/R/objective_functions.R:4-62, R-pkg/R/utils.R:93-101,171-194), %d BLAS threads.  Each timed step = "
+                      "one such evaluation at the bounded size n_s=%d (median build %.3f s + cubic part %.3f s).  value: %s.  "
+                      "The whole faithful sequence cannot run at n=%d ((q+5) 8 n^2 B = %.0f GB of temporaries)" % (
+                          threads, n_s, samples[0][1], samples[0][2], how, n, (p + 5) * 8.0 * n * n / 1e9)),
+           "sample_seconds": float(np.mean(step_s)), "seconds_per_eval_at_n": t_full, "fit": fit,
+           "lean_measured": full}
     wall = time.perf_counter() - t_start
     line = {"impl": "reference", "metric": METRIC, "value": arm["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean(step_s)) * 1e3,
-            "ms_per_step_note": "measured: one faithful evaluation at the bounded sample size n_s=%d; `value` is the "
-                                "extrapolation to n=%d described in cpu_baseline.sample" % (n_s, n),
+            "ms_per_step_note": "measured: one faithful evaluation at the bounded sample size n_s=%d; `value` is for n=%d "
+                                "as described in cpu_baseline.sample" % (n_s, n),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": config_dict(args.workload, n, args.gpus),
             "cpu_baseline": arm,
@@ -588,7 +615,7 @@ def run_ours(args):
     }
     line.update(extra)
     if world == 1 and not args.no_cpu:
-        line["cpu_baseline"] = cpu_arm_bounded(n, p, cov, seed_off, args.cpu_bounded_n)
+        line["cpu_baseline"] = cpu_baseline_gpu_arm(n, p, cov, seed_off, blas_threads())
     emit(line)
     if dist is not None:
         dist.destroy_process_group()
@@ -679,11 +706,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--n", "--problem-n", dest="n", type=int, default=0, help="override n (debug; use --problem-n under torchrun)")
-    ap.add_argument("--cpu-sample-n", type=int, default=6000, help="reference arm: size of one step's faithful evaluation")
-    ap.add_argument("--cpu-fit-n", type=lambda s: [int(v) for v in s.split(",") if v], default=[3000, 12000],
+    ap.add_argument("--cpu-sample-n", type=int, default=4000, help="reference arm: size of one step's faithful evaluation")
+    ap.add_argument("--cpu-fit-n", type=lambda s: [int(v) for v in s.split(",") if v], default=[12000],
                     help="reference arm: extra faithful sample sizes (once each) for the fitted exponent")
-    ap.add_argument("--cpu-bounded-n", type=lambda s: [int(v) for v in s.split(",") if v], default=[4000, 8000],
-                    help="GPU arm: sizes of the bounded cpu_baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-lean-full", action="store_true", help="reference arm: skip the lean in-place run at full n")
     ap.add_argument("--no-parity", action="store_true")

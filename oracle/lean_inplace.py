@@ -54,8 +54,12 @@ def build_lower_inplace(S, theta, locs, W, cov_name="exp", block=512, threads=1)
             list(ex.map(job, starts))
 
 
-def n2ll_lean_inplace(theta, locs, X, W, y, cov_name="exp", threads=1, block=512):
-    """Returns {"n2ll", "mu", "logdet", "quad", "t_build", "t_chol", "t_solve"} (profile / GLS mode)."""
+def n2ll_lean_inplace(theta, locs, X, W, y, cov_name="exp", threads=1, block=512, time_dgesv=False):
+    """Returns {"n2ll", "mu", "logdet", "quad", "t_build", "t_chol", "t_solve"} (profile / GLS mode).
+
+    time_dgesv=True additionally times ONE of the three solve(t(R), .) calls of the reference exactly as R
+    runs it (R-pkg/R/utils.R:94: La_solve -> copy of t(R), dgesv = LU with partial pivoting of the triangular
+    factor) on the factor just computed, at this n: {"t_dgesv"}.  Needs a second n x n array."""
     locs = np.asarray(locs, dtype=np.float64)
     if locs.ndim == 1:
         locs = locs[:, None]
@@ -81,5 +85,16 @@ def n2ll_lean_inplace(theta, locs, X, W, y, cov_name="exp", threads=1, block=512
     logdet = 2.0 * float(np.sum(np.log(np.diagonal(c))))
     t3 = time.perf_counter()
     val = n * math.log(2.0 * math.pi) + logdet + quad
-    return {"n2ll": val, "mu": mu, "logdet": logdet, "quad": quad,
-            "t_build": t1 - t0, "t_chol": t2 - t1, "t_solve": t3 - t2}
+    out = {"n2ll": val, "mu": mu, "logdet": logdet, "quad": quad,
+           "t_build": t1 - t0, "t_chol": t2 - t1, "t_solve": t3 - t2}
+    if time_dgesv:
+        # t(R) = L as a proper triangular matrix: the strict upper triangle was never written, zero it first
+        for j0 in range(0, n, 2048):
+            j1 = min(j0 + 2048, n)
+            blk = c[:j1, j0:j1]
+            blk[np.triu_indices(j1, 1 - j0, j1 - j0)] = 0.0
+        t4 = time.perf_counter()
+        lu, piv, x, info = lapack.dgesv(c, np.asfortranarray(X))      # overwrite_a = 0: copies t(R), as La_solve does
+        out["t_dgesv"] = time.perf_counter() - t4
+        out["dgesv_check"] = float(np.max(np.abs(x - Z[:, :p])) / max(np.max(np.abs(Z[:, :p])), 1e-300))
+    return out

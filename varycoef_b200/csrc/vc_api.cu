@@ -64,6 +64,7 @@ void vc_free_handle(vc_handle* h) {
   for (VcLane* L : h->lanes) free_lane(L);
   h->lanes.clear();
   if (h->ev_inputs) cudaEventDestroy(h->ev_inputs);
+  cudaFree(h->cb_dev);
   cudaFree(h->M.a); cudaFree(h->M.b); vc_chol_free_plans(h->cw); cudaFree(h->locs); cudaFree(h->x); cudaFree(h->w); cudaFree(h->y);
   cudaFree(h->mu_in); cudaFree(h->results); cudaFree(h->gram_dev);
   if (h->results_host) cudaFreeHost(h->results_host);
@@ -87,6 +88,18 @@ static void ensure_result_slots(vc_handle* h, int m) {
   VC_CUDA_TRY(cudaMalloc(&h->mu_in, (size_t)m * 128 * sizeof(double)));
   VC_CUDA_TRY(cudaMallocHost(&h->results_host, (size_t)m * VC_RES_STRIDE * sizeof(double)));
   h->result_slots = m;
+}
+
+void vc_set_layout(vc_handle* h, const std::vector<int>& r0, const std::vector<int>& ncols, int local_rows) {
+  h->M.a_doubles = vc_layout_fill(h->cb_host, r0, ncols, local_rows);
+  h->M.blk = h->cw.nb_tiles;
+  cudaFree(h->cb_dev);
+  h->cb_dev = nullptr;
+  VC_CUDA_TRY(cudaMalloc(&h->cb_dev, std::max<size_t>(h->cb_host.size(), 1) * sizeof(VcColBlock)));
+  if (!h->cb_host.empty())
+    VC_CUDA_TRY(cudaMemcpy(h->cb_dev, h->cb_host.data(), h->cb_host.size() * sizeof(VcColBlock), cudaMemcpyHostToDevice));
+  h->M.cb = h->cb_dev;
+  h->M.cb_host = h->cb_host.data();
 }
 
 // shared by vc_create and vc_create_dist (which passes its own local matrix shape later)
@@ -121,7 +134,6 @@ vc_handle* vc_alloc_common(const vc_config* cfg, int64_t n, int d, int p, int q,
     upload_padded(h->y, y, n, np, 1, h->st_main);
     ensure_result_slots(h, 64);
     h->M.n = n; h->M.n_pad = np; h->M.nt = (int)(np / VC_TILE);
-    h->M.lda = np + VC_BORDER_ROWS;
     h->M.nbt = 1;
     h->M.ldb = VC_BORDER_ROWS;
     h->cw.legacy_syrk = (cfg->flags & VC_FLAG_LEGACY_SYRK) != 0;
@@ -138,7 +150,12 @@ vc_handle* vc_alloc_common(const vc_config* cfg, int64_t n, int d, int p, int q,
     h->cw.lookahead = !(cfg->flags & VC_FLAG_NO_LOOKAHEAD);
     h->cw.st_main = h->st_main; h->cw.st_panel = h->st_panel;
     if (alloc_matrix) {
-      VC_CUDA_TRY(cudaMalloc(&h->M.a, (size_t)h->M.lda * np * sizeof(double)));
+      // lower block-column trapezoids only: block column c starts at row tile c * blk
+      const int blk = h->cw.nb_tiles, nt = h->M.nt;
+      std::vector<int> r0, ncols;
+      for (int c = 0; c * blk < nt; ++c) { r0.push_back(c * blk); ncols.push_back(std::min(blk, nt - c * blk)); }
+      vc_set_layout(h, r0, ncols, nt);
+      VC_CUDA_TRY(cudaMalloc(&h->M.a, (size_t)h->M.a_doubles * sizeof(double)));
       VC_CUDA_TRY(cudaMalloc(&h->M.b, (size_t)h->M.ldb * np * sizeof(double)));
       VC_CUDA_TRY(cudaMalloc(&h->cw.linv, (size_t)h->M.nt * VC_TILE * VC_TILE * sizeof(double)));
       // the diagonal-tile kernel writes only the lower 16x16 blocks of each inverse; the rest stays zero
@@ -267,7 +284,7 @@ static void make_lane(vc_handle* h) {
     L->M = h->M;
     L->M.a = nullptr; L->M.b = nullptr;
     L->M.nbt = 1; L->M.ldb = VC_BORDER_ROWS;
-    VC_CUDA_TRY(cudaMalloc(&L->M.a, (size_t)L->M.lda * np * sizeof(double)));
+    VC_CUDA_TRY(cudaMalloc(&L->M.a, (size_t)L->M.a_doubles * sizeof(double)));
     VC_CUDA_TRY(cudaMalloc(&L->M.b, (size_t)L->M.ldb * np * sizeof(double)));
     L->cw.nb_tiles = h->cw.nb_tiles; L->cw.lookahead = h->cw.lookahead;
     L->cw.legacy_syrk = h->cw.legacy_syrk; L->cw.legacy_potrf = h->cw.legacy_potrf; L->cw.num_sms = h->cw.num_sms;

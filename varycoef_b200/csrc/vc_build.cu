@@ -32,7 +32,8 @@ struct BuildArgs {
   const double* locs;   // n_pad x d
   const double* w;      // n_pad x q
   const int* tiles;     // optional list of packed (I | J << 16) global tiles (distributed build)
-  int blk, pr, pc;      // block-cyclic distribution of the OUTPUT (0 = plain)
+  const VcColBlock* cb; // block-column storage of the OUTPUT (lower tiles); nullptr = dense `out` with `ld` (FULL)
+  int blk, pr, pc;      // tiles per storage block; process grid of a block-cyclic output (1 x 1 = plain)
   VcTheta th;
 };
 
@@ -80,10 +81,14 @@ __global__ void __launch_bounds__(BUILD_THREADS) k_build(BuildArgs p) {
   const int rg = tid & 63, cg = tid >> 6;
   const int r0 = 2 * rg;
   const int64_t gi0 = (int64_t)I * TILE + r0;
-  // position in the (possibly block-cyclic local) output
-  const int lI = p.blk ? ((I / p.blk) / p.pr) * p.blk + I % p.blk : I;
-  const int lJ = p.blk ? ((J / p.blk) / p.pc) * p.blk + J % p.blk : J;
-  const int64_t oi0 = (int64_t)lI * TILE + r0, oj0 = (int64_t)lJ * TILE;
+  // position in the (possibly block-cyclic local) block-column storage
+  double* otile = nullptr;
+  int64_t old_ = 0;
+  if (!FULL) {
+    const int lI = p.pr > 1 ? ((I / p.blk) / p.pr) * p.blk + I % p.blk : I;
+    const int lJ = p.pc > 1 ? ((J / p.blk) / p.pc) * p.blk + J % p.blk : J;
+    otile = vc_tile_ptr(p.out, p.cb, p.blk, lI, lJ, old_) + r0;
+  }
   const int method = p.th.dist_method;
   const double mink = p.th.mink_p;
 
@@ -157,7 +162,7 @@ __global__ void __launch_bounds__(BUILD_THREADS) k_build(BuildArgs p) {
         if (gi0 + 1 < p.n) p.out[gi0 + 1 + gj * p.ld] = v1;
       }
     } else {
-      *reinterpret_cast<double2*>(p.out + oi0 + (oj0 + j) * p.ld) = make_double2(v0, v1);
+      *reinterpret_cast<double2*>(otile + (int64_t)j * old_) = make_double2(v0, v1);
     }
   }
 }
@@ -205,9 +210,10 @@ __global__ void __launch_bounds__(BUILD_THREADS, 3) k_build_fast(BuildArgs p) {
     ir[k] = p.th.inv_range[k];
     sk[k] = p.th.sill[k];
   }
-  const int lI = p.blk ? ((I / p.blk) / p.pr) * p.blk + I % p.blk : I;
-  const int lJ = p.blk ? ((J / p.blk) / p.pc) * p.blk + J % p.blk : J;
-  double* out = p.out + (int64_t)lI * TILE + r0 + (int64_t)lJ * TILE * p.ld;
+  const int lI = p.pr > 1 ? ((I / p.blk) / p.pr) * p.blk + I % p.blk : I;
+  const int lJ = p.pc > 1 ? ((J / p.blk) / p.pc) * p.blk + J % p.blk : J;
+  int64_t old_;
+  double* out = vc_tile_ptr(p.out, p.cb, p.blk, lI, lJ, old_) + r0;
   const int taper_id = p.th.taper_id;
   const double inv_delta = p.th.inv_delta;
   __syncthreads();
@@ -237,7 +243,7 @@ __global__ void __launch_bounds__(BUILD_THREADS, 3) k_build_fast(BuildArgs p) {
     }
     if (gi0 == gj) v0 += (gj < p.n) ? p.th.tau2 : 1.0;
     if (gi0 + 1 == gj) v1 += (gj < p.n) ? p.th.tau2 : 1.0;
-    *reinterpret_cast<double2*>(out + (int64_t)j * p.ld) = make_double2(v0, v1);
+    *reinterpret_cast<double2*>(out + (int64_t)j * old_) = make_double2(v0, v1);
   }
 }
 
@@ -322,21 +328,21 @@ void vc_build_init() {
 void vc_launch_build(const VcMatrix& M, const VcTheta& th, int d, const double* locs_pad,
                      const double* w_pad, cudaStream_t st, int64_t* launches) {
   BuildArgs a{};
-  a.out = M.a; a.ld = M.lda; a.n = M.n; a.n_pad = M.n_pad; a.nt = M.nt; a.d = d;
+  a.out = M.a; a.cb = M.cb; a.blk = M.blk; a.pr = 1; a.pc = 1; a.n = M.n; a.n_pad = M.n_pad; a.nt = M.nt; a.d = d;
   a.locs = locs_pad; a.w = w_pad; a.th = th;
   launch_build_t<false>(a, st);
   ++*launches;
 }
 
 // distributed build: only the listed global tiles, written at their block-cyclic local position
-void vc_launch_build_tiles(double* a_loc, int64_t lda_loc, int64_t n, int64_t n_pad, const VcTheta& th, int d,
+void vc_launch_build_tiles(const VcMatrix& M, const VcTheta& th, int d,
                            const double* locs_pad, const double* w_pad, const int* tiles, int ntiles,
-                           int blk, int pr, int pc, cudaStream_t st, int64_t* launches) {
+                           int pr, int pc, cudaStream_t st, int64_t* launches) {
   if (ntiles <= 0) return;
   BuildArgs a{};
-  a.out = a_loc; a.ld = lda_loc; a.n = n; a.n_pad = n_pad; a.nt = (int)(n_pad / TILE); a.d = d;
+  a.out = M.a; a.cb = M.cb; a.n = M.n; a.n_pad = M.n_pad; a.nt = M.nt; a.d = d;
   a.locs = locs_pad; a.w = w_pad; a.th = th;
-  a.tiles = tiles; a.blk = blk; a.pr = pr; a.pc = pc;
+  a.tiles = tiles; a.blk = M.blk; a.pr = pr; a.pc = pc;
   launch_build_t<false>(a, st, (unsigned)ntiles);
   ++*launches;
 }
@@ -369,6 +375,7 @@ void vc_launch_sigma_full(double* out, int64_t n, int64_t n_pad, const VcTheta& 
   BuildArgs a{};
   a.out = out; a.ld = n; a.n = n; a.n_pad = n_pad; a.nt = (int)(n_pad / TILE); a.d = d;
   a.locs = locs_pad; a.w = w_pad; a.th = th;
+  a.blk = 1; a.pr = 1; a.pc = 1;
   launch_build_t<true>(a, st);
   ++*launches;
 }

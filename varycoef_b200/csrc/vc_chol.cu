@@ -98,13 +98,13 @@ using GemmArgs = VcGemmArgs;
 
 // local tile index of global tile t in a block-cyclic distribution over P processes
 __device__ __forceinline__ int loc_tile(const GemmArgs& p, int t, int P) {
-  return p.blk ? ((t / p.blk) / P) * p.blk + t % p.blk : t;
+  return P > 1 ? ((t / p.blk) / P) * p.blk + t % p.blk : t;
 }
 // pointer to element (0, col) of row tile I in the (local) matrix / border; col in LOCAL elements
 __device__ __forceinline__ double* row_tile_ptr(const GemmArgs& p, int I, int64_t col, int64_t& ld) {
   if (I < p.nt) {
-    ld = p.lda;
-    return p.a + (int64_t)loc_tile(p, I, p.pr) * TILE + col * p.lda;
+    double* t = vc_tile_ptr(p.a, p.cb, p.blk, loc_tile(p, I, p.pr), (int)(col >> 7), ld);
+    return t + (col & (TILE - 1)) * ld;
   }
   ld = p.ldb;
   return p.b + (int64_t)(I - p.nt) * TILE + col * p.ldb;
@@ -1240,6 +1240,21 @@ void build_plan(VcCholPlan& pl, int nt, int nbt, int nb, bool lookahead, int mod
 
 }  // namespace
 
+int64_t vc_layout_fill(std::vector<VcColBlock>& cb, const std::vector<int>& r0, const std::vector<int>& ncols,
+                       int local_rows) {
+  cb.resize(r0.size());
+  int64_t off = 0;
+  for (size_t c = 0; c < r0.size(); ++c) {
+    const int rows = std::max(local_rows - r0[c], 0);
+    const int ld_tiles = std::max(rows, 1) | 1;        // odd: the column stride is never a multiple of 2 KB
+    cb[c].off = off;
+    cb[c].ld = ld_tiles * VC_TILE;
+    cb[c].r0 = r0[c];
+    off += (int64_t)cb[c].ld * ncols[c] * VC_TILE;
+  }
+  return std::max<int64_t>(off, 1);
+}
+
 void vc_chol_init() {
   static bool done_dev[64] = {false};
   int dev = 0;
@@ -1268,9 +1283,10 @@ static bool potrf_use_b() {
 void vc_chol_invert_diag_tiles(const VcMatrix& M, VcCholWork& w, int64_t* launches) {
   vc_launch_reset_info(w.info, w.st_main, launches);
   for (int jt = 0; jt < M.nt; ++jt) {
-    double* diag = M.a + (int64_t)jt * TILE * (M.lda + 1);
-    if (potrf_use_b()) k_potrf128b<false><<<1, POTRF_THREADS, POTRFB_SMEM, w.st_main>>>(diag, M.lda, jt, w.linv, w.logdet_part, w.info);
-    else k_potrf128c<false><<<1, POTRF_THREADS, POTRFC_SMEM, w.st_main>>>(diag, M.lda, jt, w.linv, w.logdet_part, w.info);
+    int64_t ld;
+    double* diag = vc_host_tile_ptr(M, jt, jt, &ld);
+    if (potrf_use_b()) k_potrf128b<false><<<1, POTRF_THREADS, POTRFB_SMEM, w.st_main>>>(diag, ld, jt, w.linv, w.logdet_part, w.info);
+    else k_potrf128c<false><<<1, POTRF_THREADS, POTRFC_SMEM, w.st_main>>>(diag, ld, jt, w.linv, w.logdet_part, w.info);
     ++*launches;
   }
 }
@@ -1387,7 +1403,7 @@ void vc_append_trapezoid(std::vector<int>& out, int J0, int J1, int nrows) { app
 
 static GemmArgs base_args(const VcMatrix& M) {
   GemmArgs g{};
-  g.a = M.a; g.lda = M.lda; g.b = M.b; g.ldb = M.ldb; g.nt = M.nt;
+  g.a = M.a; g.cb = M.cb; g.blk = M.blk; g.pr = 1; g.pc = 1; g.b = M.b; g.ldb = M.ldb; g.nt = M.nt;
   return g;
 }
 
@@ -1431,6 +1447,8 @@ int vc_pick_reserved_sms(int num_sms, int rows_t /*row tiles below the panel*/, 
 }
 void vc_chol_factor(const VcMatrix& M, VcCholWork& w, int64_t* launches, int mode) {
   const int nt = M.nt, nbt = M.nbt, nb = w.nb_tiles;
+  // a K-panel of the trailing update must lie inside ONE storage block column (uniform leading dimension)
+  if (nb != M.blk) throw VcError(VC_ERR_INVALID, "outer Cholesky block differs from the storage block of the matrix");
   const bool solve = (mode != VC_SWEEP_FACTOR);
   const bool la = w.lookahead && !solve;
   VcCholPlan& pl = solve ? w.plan_solve : w.plan_factor;
@@ -1461,8 +1479,9 @@ void vc_chol_factor(const VcMatrix& M, VcCholWork& w, int64_t* launches, int mod
     size_t call = first_call[ob / nb];
     for (int jt = ob; jt < oe; ++jt) {
       if (!solve) {
-        double* diag = M.a + (int64_t)jt * TILE * (M.lda + 1);
-        vc_launch_potrf(diag, M.lda, jt, w.linv, w.logdet_part, w.info, w.legacy_potrf, sp, launches);
+        int64_t ld;
+        double* diag = vc_host_tile_ptr(M, jt, jt, &ld);
+        vc_launch_potrf(diag, ld, jt, w.linv, w.logdet_part, w.info, w.legacy_potrf, sp, launches);
       }
       GemmArgs g = base_args(M);
       g.linv = w.linv + (int64_t)jt * TILE * TILE;

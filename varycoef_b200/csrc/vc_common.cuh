@@ -51,10 +51,46 @@ struct VcError {
   VcError(int c, const std::string& m) : code(c), msg(m) {}
 };
 
+// ---- storage of the lower triangle ----------------------------------------------------------
+// Only the lower trapezoid of every BLOCK COLUMN is stored (blk tile columns wide; blk = the outer
+// Cholesky block = the distribution block of the sharded path): block column c holds the row tiles
+// [r0, rows) of its columns, column-major with its own leading dimension (an odd number of 128-double
+// tiles, so that no column stride is a multiple of 2 KB).  Tile (lI, lJ) in LOCAL tile indices:
+//   a + cb[lJ / blk].off + (lI - r0) * 128 + ((lJ % blk) * 128 + col) * ld
+// n = 50 000: 10.3 GB instead of 20.1 GB for the full square; n = 150 000: 91 GB -- fits one B200.
+struct VcColBlock {
+  int64_t off;           // doubles from the start of the allocation to (row tile r0, first column)
+  int32_t ld;            // leading dimension in doubles
+  int32_t r0;            // first LOCAL row tile stored in this block column
+};
+#if defined(__CUDACC__)
+__device__ __forceinline__ double* vc_tile_ptr(double* a, const VcColBlock* __restrict__ cb, int blk, int lI, int lJ,
+                                               int64_t& ld) {
+  const int c = lJ / blk;
+  const longlong2 e0 = __ldg(reinterpret_cast<const longlong2*>(cb + c));   // one 16-byte load: off | (ld, r0)
+  const int eld = (int)(e0.y & 0xffffffffll), er0 = (int)(e0.y >> 32);
+  ld = eld;
+  return a + e0.x + (int64_t)(lI - er0) * VC_TILE + (int64_t)(lJ - c * blk) * VC_TILE * (int64_t)eld;
+}
+// element (i, j), i >= j, of a NON-distributed matrix
+__device__ __forceinline__ double* vc_elem_ptr(double* a, const VcColBlock* __restrict__ cb, int blk, int64_t i, int64_t j) {
+  int64_t ld;
+  double* t = vc_tile_ptr(a, cb, blk, (int)(i >> 7), (int)(j >> 7), ld);
+  return t + (i & (VC_TILE - 1)) + (j & (VC_TILE - 1)) * ld;
+}
+#endif
+// fills `cb` for block columns whose first stored local row tile is r0[c]; local_rows = row tiles held.
+// Returns the number of doubles to allocate.  ncols[c] = tile columns of block column c (<= blk).
+int64_t vc_layout_fill(std::vector<VcColBlock>& cb, const std::vector<int>& r0, const std::vector<int>& ncols,
+                       int local_rows);
+
 // ---- launchers implemented in the .cu files ------------------------------------------------
-struct VcMatrix {        // padded, column-major Sigma / factor in HBM, plus its border rows
-  double* a;             // lda x n_pad, lower triangle used
-  int64_t lda;           // n_pad + 128 (keeps the column stride off a power of two)
+struct VcMatrix {        // padded Sigma / factor in HBM (lower block-column trapezoids), plus its border rows
+  double* a;
+  const VcColBlock* cb;       // device table, one entry per local block column
+  const VcColBlock* cb_host;  // the same table on the host (owned by the handle)
+  int blk;               // tile columns per block column
+  int64_t a_doubles;     // size of the allocation behind `a`
   int64_t n;             // real order
   int64_t n_pad;         // multiple of VC_TILE
   int nt;                // n_pad / VC_TILE  (column tiles)
@@ -72,9 +108,9 @@ void vc_launch_sigma_full(double* out, int64_t n, int64_t n_pad, const VcTheta& 
                           const double* locs_pad, const double* w_pad, cudaStream_t st,
                           int64_t* launches);
 void vc_build_init();
-void vc_launch_build_tiles(double* a_loc, int64_t lda_loc, int64_t n, int64_t n_pad, const VcTheta& th, int d,
+void vc_launch_build_tiles(const VcMatrix& M, const VcTheta& th, int d,
                            const double* locs_pad, const double* w_pad, const int* tiles, int ntiles,
-                           int blk, int pr, int pc, cudaStream_t st, int64_t* launches);
+                           int pr, int pc, cudaStream_t st, int64_t* launches);
 void vc_launch_border_dist(double* b, int64_t ldb, int64_t n_pad, int p, const double* x_pad,
                            const double* y_pad, const int* col_tiles_dev, int nloc, cudaStream_t st,
                            int64_t* launches);
@@ -89,11 +125,11 @@ struct VcOpSrc {          // where a GEMM operand row tile comes from
 };
 struct VcGemmArgs {       // by-value argument block of k_trsm_panel / k_syrk_ws / k_syrk_tiles
   double* a;              // (local) matrix, row tiles 0 .. nt-1 (global numbering)
-  int64_t lda;
+  const VcColBlock* cb;   // its block-column table
   double* b;              // border rows, row tiles nt .. nt+nbt-1
   int64_t ldb;
   int nt;
-  int blk, pr, pc;        // block-cyclic distribution: tiles per block (0 = not distributed), grid
+  int blk, pr, pc;        // tiles per (storage = distribution) block; process grid (1 x 1 = not distributed)
   const double* linv;     // TRSM: 128x128 inverse factor (ld 128)
   int k0;                 // first panel column in LOCAL elements (operands taken from the matrix)
   int K;                  // panel depth (multiple of 16)
@@ -137,6 +173,12 @@ void vc_chol_factor(const VcMatrix& M, VcCholWork& w, int64_t* launches, int mod
 void vc_chol_free_plans(VcCholWork& w);
 void vc_chol_invert_diag_tiles(const VcMatrix& M, VcCholWork& w, int64_t* launches);
 // raw launchers (used by the distributed driver, vc_dist.cu)
+// host-side address of local tile (lI, lJ)
+inline double* vc_host_tile_ptr(const VcMatrix& M, int lI, int lJ, int64_t* ld) {
+  const VcColBlock& e = M.cb_host[lJ / M.blk];
+  *ld = e.ld;
+  return M.a + e.off + (int64_t)(lI - e.r0) * VC_TILE + (int64_t)(lJ % M.blk) * VC_TILE * (int64_t)e.ld;
+}
 void vc_launch_potrf(double* diag, int64_t lda, int jt, double* linv_all, double* logdet_part, int* info,
                      bool legacy, cudaStream_t st, int64_t* launches);
 void vc_launch_trsm(const VcGemmArgs& g, int grid, cudaStream_t st, int64_t* launches);

@@ -140,7 +140,6 @@ struct VcDist {
   ncclComm_t comm = nullptr;
   int nt = 0, nbt = 1, nb = 4;
   int lrt = 0, lct = 0;
-  int64_t lda = 0;
   std::vector<int> col_tiles;
   int* col_tiles_dev = nullptr;
   int* tiles_dev = nullptr;
@@ -286,11 +285,20 @@ extern "C" int vc_create_dist(vc_handle** out, const vc_config* cfg_in, int64_t 
       }
     }
     D->lrt = lrt; D->lct = lct;
-    D->lda = (int64_t)std::max(lrt, 1) * VC_TILE + VC_TILE;
-    h->M.lda = D->lda;
+    // local storage: only the lower trapezoid of every local block column.  Local block column lc is global
+    // block Bj = lc * pc + my_pc; the first local row block with global index >= Bj is ceil((Bj - my_pr) / pr).
+    {
+      std::vector<int> r0, ncols;
+      for (int b = D->my_pc; b < nblocks; b += pc) {
+        const int first = b <= D->my_pr ? 0 : (b - D->my_pr + pr - 1) / pr;
+        r0.push_back(std::min(first * nb, lrt));
+        ncols.push_back(std::min(nb, nt - b * nb));
+      }
+      vc_set_layout(h, r0, ncols, lrt);
+    }
     h->M.ldb = VC_BORDER_ROWS;
     h->M.nbt = 1;
-    VC_CUDA_TRY(cudaMalloc(&h->M.a, (size_t)D->lda * std::max(lct, 1) * VC_TILE * sizeof(double)));
+    VC_CUDA_TRY(cudaMalloc(&h->M.a, (size_t)h->M.a_doubles * sizeof(double)));
     VC_CUDA_TRY(cudaMalloc(&h->M.b, (size_t)h->M.ldb * std::max(lct, 1) * VC_TILE * sizeof(double)));
     VC_CUDA_TRY(cudaMalloc(&h->cw.logdet_part, (size_t)nt * sizeof(double)));
     VC_CUDA_TRY(cudaMalloc(&D->col_tiles_dev, std::max<size_t>(D->col_tiles.size(), 1) * sizeof(int)));
@@ -338,14 +346,14 @@ int vc_dist_n2ll(vc_handle* h, const double* theta, int32_t mu_mode, const doubl
     VC_CUDA_TRY(cudaEventRecord(h->ev[0], st));
     VC_CUDA_TRY(cudaMemsetAsync(h->cw.logdet_part, 0, (size_t)nt * sizeof(double), st));
     vc_launch_reset_info(h->cw.info, st, &h->launches);
-    vc_launch_build_tiles(h->M.a, h->M.lda, h->n, h->n_pad, th, h->d, h->locs, h->w,
-                          D->tiles_dev + D->build.off, D->build.n, nb, D->pr, D->pc, st, &h->launches);
+    vc_launch_build_tiles(h->M, th, h->d, h->locs, h->w,
+                          D->tiles_dev + D->build.off, D->build.n, D->pr, D->pc, st, &h->launches);
     if (D->my_pr == 0)
       vc_launch_border_dist(h->M.b, h->M.ldb, h->n_pad, p, h->x, h->y, D->col_tiles_dev, D->lct, st, &h->launches);
     VC_CUDA_TRY(cudaEventRecord(h->ev[1], st));
 
     VcGemmArgs base{};
-    base.a = h->M.a; base.lda = h->M.lda; base.b = h->M.b; base.ldb = h->M.ldb; base.nt = nt;
+    base.a = h->M.a; base.cb = h->M.cb; base.b = h->M.b; base.ldb = h->M.ldb; base.nt = nt;
     base.blk = nb; base.pr = D->pr; base.pc = D->pc;
     // Lookahead: the panel phase of block s+1 (factor / broadcasts / solves, stream sp) overlaps the
     // "rest" part of the trailing update of block s (stream sm).  All NCCL calls are on sp, in the
@@ -367,10 +375,10 @@ int vc_dist_n2ll(vc_handle* h, const double* theta, int32_t mu_mode, const doubl
       if (D->rank == s.diag_owner) {
         for (int jt = s.ob; jt < s.oe; ++jt) {
           const int k = jt - s.ob;
-          double* diag = h->M.a + (int64_t)loc_tile_h(jt, nb, D->pr) * VC_TILE +
-                         (int64_t)loc_tile_h(jt, nb, D->pc) * VC_TILE * h->M.lda;
+          int64_t ldd;
+          double* diag = vc_host_tile_ptr(h->M, loc_tile_h(jt, nb, D->pr), loc_tile_h(jt, nb, D->pc), &ldd);
           // potrf indexes its inverse slot by jt: bias the base so that slot jt is dd_linv[jt - ob]
-          vc_launch_potrf(diag, h->M.lda, jt, dd_linv - (int64_t)s.ob * VC_TILE * VC_TILE, h->cw.logdet_part,
+          vc_launch_potrf(diag, ldd, jt, dd_linv - (int64_t)s.ob * VC_TILE * VC_TILE, h->cw.logdet_part,
                           h->cw.info, h->cw.legacy_potrf, sp, &h->launches);
           VcGemmArgs g = base;
           g.linv = dd_linv + (size_t)k * VC_TILE * VC_TILE;

@@ -34,8 +34,8 @@ __global__ void k_set_identity(double* b, int64_t ldb, int64_t n_pad) {
 }
 
 // a(i, j) = R(j, i) for i >= j (L = R^T), unit diagonal / zeros in the padding
-__global__ void k_load_factor(const double* __restrict__ R, int64_t n, double* __restrict__ a, int64_t lda,
-                              int64_t n_pad) {
+__global__ void k_load_factor(const double* __restrict__ R, int64_t n, double* __restrict__ a,
+                              const VcColBlock* __restrict__ cb, int blk, int64_t n_pad) {
   __shared__ double t[32][33];
   const int64_t bi = (int64_t)blockIdx.x * 32, bj = (int64_t)blockIdx.y * 32;   // block of a: rows bi.., cols bj..
   if (bi + 31 < bj) return;
@@ -50,7 +50,7 @@ __global__ void k_load_factor(const double* __restrict__ R, int64_t n, double* _
     if (i < n_pad && j < n_pad && i >= j) {
       double v = t[tx][yy];
       if (i >= n || j >= n) v = (i == j) ? 1.0 : 0.0;
-      a[i + j * lda] = v;
+      *vc_elem_ptr(a, cb, blk, i, j) = v;
     }
   }
 }
@@ -101,13 +101,14 @@ __global__ void __launch_bounds__(128) k_bs_diag(const double* __restrict__ linv
   r[c] = s;
 }
 // r_k -= L(jt, k)^T alpha_jt for every k < jt (one CTA per k)
-__global__ void __launch_bounds__(128) k_bs_update(const double* __restrict__ a, int64_t lda, int jt,
+__global__ void __launch_bounds__(128) k_bs_update(double* a, const VcColBlock* __restrict__ cb, int blk, int jt,
                                                    double* __restrict__ r) {
   __shared__ double al[TILE];
   const int k = blockIdx.x, c = threadIdx.x;
   al[c] = r[(int64_t)jt * TILE + c];
   __syncthreads();
-  const double* col = a + (int64_t)jt * TILE + ((int64_t)k * TILE + c) * lda;
+  int64_t lda;
+  const double* col = vc_tile_ptr(a, cb, blk, jt, k, lda) + (int64_t)c * lda;
   double s = 0.0;
 #pragma unroll 8
   for (int i = 0; i < TILE; ++i) s = fma(col[i], al[i], s);
@@ -358,7 +359,7 @@ extern "C" int vc_predict(vc_handle* h, const double* theta, const double* mu, i
     k_resid<<<(unsigned)((np + 255) / 256), 256, 0, st>>>(h->M.b, h->M.ldb, np, p, mud.p, rz.p);
     for (int jt = h->M.nt - 1; jt >= 0; --jt) {
       k_bs_diag<<<1, 128, 0, st>>>(h->cw.linv + (size_t)jt * TILE * TILE, rz.p + (size_t)jt * TILE);
-      if (jt > 0) k_bs_update<<<jt, 128, 0, st>>>(h->M.a, h->M.lda, jt, rz.p);
+      if (jt > 0) k_bs_update<<<jt, 128, 0, st>>>(h->M.a, h->M.cb, h->M.blk, jt, rz.p);
     }
     h->launches += 1 + 2 * h->M.nt;
     // eff[i, k] = sum_j cov_k(d(new_i, s_j)) taper W_jk alpha_j   (Sigma_b_y %*% alpha, R-pkg/R/utils.R:238-249)
@@ -436,7 +437,7 @@ extern "C" int vc_gls_chol(int32_t device, int64_t n, int32_t p, const double* R
       DevBuf Rd((size_t)n * n);
       VC_CUDA_TRY(cudaMemcpyAsync(Rd.p, R, (size_t)n * n * sizeof(double), cudaMemcpyHostToDevice, st));
       dim3 grid((unsigned)((h->n_pad + 31) / 32), (unsigned)((h->n_pad + 31) / 32));
-      k_load_factor<<<grid, dim3(32, 8), 0, st>>>(Rd.p, n, h->M.a, h->M.lda, h->n_pad);
+      k_load_factor<<<grid, dim3(32, 8), 0, st>>>(Rd.p, n, h->M.a, h->M.cb, h->M.blk, h->n_pad);
       VC_CUDA_TRY(cudaStreamSynchronize(st));
     }
     vc_chol_invert_diag_tiles(h->M, h->cw, &h->launches);

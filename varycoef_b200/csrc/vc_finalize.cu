@@ -201,13 +201,13 @@ __global__ void k_gather_whitened(const double* __restrict__ b, int64_t ldb, int
 }
 
 // R = L^T as base::chol returns it: upper triangular n x n, zeros below the diagonal
-__global__ void k_extract_chol(const double* __restrict__ a, int64_t lda, int64_t n, double* __restrict__ r) {
+__global__ void k_extract_chol(double* a, const VcColBlock* __restrict__ cb, int blk, int64_t n, double* __restrict__ r) {
   __shared__ double t[32][33];
   const int64_t bi = (int64_t)blockIdx.x * 32, bj = (int64_t)blockIdx.y * 32;   // block of L: rows bi.., cols bj..
   const int tx = threadIdx.x, ty = threadIdx.y;
   for (int yy = ty; yy < 32; yy += 8) {
     const int64_t i = bi + tx, j = bj + yy;
-    t[yy][tx] = (i < n && j < n && i >= j) ? a[i + j * lda] : 0.0;
+    t[yy][tx] = (i < n && j < n && i >= j) ? *vc_elem_ptr(a, cb, blk, i, j) : 0.0;
   }
   __syncthreads();
   for (int yy = ty; yy < 32; yy += 8) {
@@ -306,6 +306,6 @@ void vc_launch_gather_whitened(const VcMatrix& M, int p, double* z_out_dev, cuda
 
 void vc_launch_extract_chol(const VcMatrix& M, double* r_out_dev, cudaStream_t st, int64_t* launches) {
   dim3 grid((unsigned)((M.n + 31) / 32), (unsigned)((M.n + 31) / 32));
-  k_extract_chol<<<grid, dim3(32, 8), 0, st>>>(M.a, M.lda, M.n, r_out_dev);
+  k_extract_chol<<<grid, dim3(32, 8), 0, st>>>(M.a, M.cb, M.blk, M.n, r_out_dev);
   ++*launches;
 }

@@ -21,6 +21,8 @@ struct vc_handle {
   int d = 0, p = 0, q = 0;
   int device = 0;
   VcMatrix M{};
+  std::vector<VcColBlock> cb_host;   // block-column storage table of M (and of every lane); device copy in cb_dev
+  VcColBlock* cb_dev = nullptr;
   // O(n) inputs, zero-padded to n_pad, column-major
   double *locs = nullptr, *x = nullptr, *w = nullptr, *y = nullptr;
   double* mu_in = nullptr;           // staging for caller-supplied mu (p x slots)
@@ -50,4 +52,6 @@ vc_handle* vc_alloc_common(const vc_config* cfg, int64_t n, int d, int p, int q,
                            const double* X, const double* W, const double* y, bool alloc_matrix);
 void vc_free_handle(vc_handle* h);
 int vc_fail(vc_handle* h, int code, const std::string& msg);
+// computes the layout (r0 / ncols per local block column, local_rows row tiles), uploads the table and points M at it
+void vc_set_layout(vc_handle* h, const std::vector<int>& r0, const std::vector<int>& ncols, int local_rows);
 int vc_validate_cfg(const vc_config* cfg, int64_t n, int d, int p, int q, std::string& why);
