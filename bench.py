@@ -648,7 +648,13 @@ def run_dist(args):
     K, Wm = args.steps, args.warmup
     peak_tf = C.c_double(0.0)
     _lib.lib().vc_probe_dmma_peak(local, 20000, C.byref(peak_tf))
-    obj = distributed_objective(y, X, locs, cov_name=cov, profileLik=True, device=local, nb_outer=args.nb)
+    if world == 1 and not args.force_dist:
+        # lower block-column storage: n = 150 000 (91 GB) fits ONE B200 -- the plain single-GPU path is the N = 1
+        # point of the strong-scaling curve and the bit-exact parity reference of the sharded runs
+        from varycoef_b200 import SVCObjective
+        obj = SVCObjective(y, X, locs, cov_name=cov, profileLik=True, device=local, nb_outer=args.nb)
+    else:
+        obj = distributed_objective(y, X, locs, cov_name=cov, profileLik=True, device=local, nb_outer=args.nb)
     for s in range(Wm):
         obj.n2LL(thetas[s % len(thetas)])
     sampler = ClockSampler(local)
@@ -683,7 +689,8 @@ def run_dist(args):
                 "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": elapsed / K * 1e3,
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": desc, "n": n, "p": p, "q": q, "cov": cov, "grid": "%dx%d" % (pr, pc), "nb_outer": args.nb or "auto",
-                           "parallelism": "2D block-cyclic Sigma_y, NCCL panel broadcasts, lookahead",
+                           "parallelism": ("2D block-cyclic Sigma_y, NCCL panel broadcasts, lookahead" if world > 1 or args.force_dist
+                                           else "single GPU (plain path, lower block-column storage)"),
                            "l2": "inputs larger than L2"},
                 "clocks": clocks, "gpu_launches": launches,
                 "e2e": {"value": K / elapsed, "unit": UNIT, "h2d_bytes_per_step": 8 * (2 * q + 1), "d2h_bytes_per_step": 8 * 132,
@@ -717,6 +724,7 @@ def main():
     ap.add_argument("--sharded-n", type=int, default=0, help="override n of the sharded record (debug)")
     ap.add_argument("--sharded-steps", type=int, default=2)
     ap.add_argument("--nb", type=int, default=0, help="outer Cholesky block (0 = auto)")
+    ap.add_argument("--force-dist", action="store_true", help="--workload c4 at N = 1: use the block-cyclic driver on a 1x1 grid")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -207,8 +207,9 @@ def test_batch_equals_single_and_is_deterministic():
 
 @pytest.mark.parametrize("n,m,reps", [(1000, 17, 12), (2000, 17, 8), (5000, 13, 4), (10000, 9, 2)])
 def test_batch_equals_single_stress(n, m, reps):
-    """Evaluation lanes share the persistent update kernel, the streams and the events of the handle: a latent
-    race would show up as a batch value that differs from the one-at-a-time value.  Repeated, bit-exact."""
+    """A batch is swept by ONE sequence of launches with the evaluation slot in the grid (vc_api.cu): every slot
+    must reproduce the one-at-a-time value bit for bit -- a wrong slot stride, a race between slots in the
+    persistent update kernel or a stale slot would show up here.  Repeated."""
     from varycoef_b200 import SVCObjective
     locs, X, W, y = synth(n, 3, 100 + n, 2)
     base = theta_for(3)
@@ -217,9 +218,43 @@ def test_batch_equals_single_stress(n, m, reps):
         single = np.array([obj.n2LL(x) for x in xs])
         for _ in range(reps):
             assert np.array_equal(single, obj.n2LL_batch(xs))
-        # and interleaved: a single evaluation between batches must not disturb the lanes
+        # and interleaved: a single evaluation between batches must not disturb the slots
         assert obj.n2LL(xs[3]) == single[3]
         assert np.array_equal(single, obj.n2LL_batch(xs))
+
+
+def test_batch_shares_factorisations_of_repeated_thetas():
+    """optim's stencil of the NON-profile objective (the reference's default, profileLik = FALSE) repeats theta
+    for every probe of a mean parameter: those evaluations share one factorisation and differ only in the finalize.
+    Values must equal the one-at-a-time ones bit for bit, in any order, with invalid points in between."""
+    from varycoef_b200 import SVCObjective
+    n, p = 1400, 3
+    locs, X, W, y = synth(n, p, 41, 2)
+    th = theta_for(p)
+    rng = np.random.default_rng(3)
+    mus = rng.standard_normal((9, p))
+    thetas = [th, th * 1.01, th, th * 0.99, th * 1.01, th, th * 1.02, th, th * 1.01]
+    xs = np.array([np.concatenate([t, m]) for t, m in zip(thetas, mus)])
+    bad = xs[4].copy()
+    bad[0] = -1.0
+    xs_bad = np.vstack([xs[:4], bad, xs[5:]])
+    with SVCObjective(y, X, locs, profileLik=False) as obj:
+        single = np.array([obj.n2LL(x) for x in xs])
+        l0 = obj.launch_count
+        batch = obj.n2LL_batch(xs)
+        l_batch = obj.launch_count - l0
+        assert np.array_equal(single, batch)
+        vals, status = obj.n2LL_batch(xs_bad, return_status=True)
+        assert list(status) == [0, 0, 0, 0, 2, 0, 0, 0, 0] and np.isnan(vals[4])
+        assert np.array_equal(np.delete(vals, 4), np.delete(single, 4))
+        # 4 distinct thetas: the batch must cost far fewer launches than 9 separate evaluations
+        l0 = obj.launch_count
+        for x in xs:
+            obj.n2LL(x * (1 + 1e-9))
+        assert l_batch < 0.7 * (obj.launch_count - l0)
+        # the factor left in slot 0 is the one of the LAST evaluation
+        last = obj.n2LL(xs[-1])
+        assert last == single[-1]
 
 
 @pytest.mark.parametrize("cov,n,dim", [("mat52", 1200, 2), ("mat32", 1000, 2), ("exp", 800, 1), ("mat52", 700, 1)])

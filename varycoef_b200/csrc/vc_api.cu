@@ -55,18 +55,17 @@ int vc_validate_cfg(const vc_config* cfg, int64_t n, int d, int p, int q, std::s
   return VC_OK;
 }
 
-static void free_lane(VcLane* L);
-
 void vc_free_handle(vc_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   if (h->dist) vc_dist_destroy(h);
-  for (VcLane* L : h->lanes) free_lane(L);
-  h->lanes.clear();
-  if (h->ev_inputs) cudaEventDestroy(h->ev_inputs);
   cudaFree(h->cb_dev);
   cudaFree(h->M.a); cudaFree(h->M.b); vc_chol_free_plans(h->cw); cudaFree(h->locs); cudaFree(h->x); cudaFree(h->w); cudaFree(h->y);
   cudaFree(h->mu_in); cudaFree(h->results); cudaFree(h->gram_dev);
+  cudaFree(h->thetas_dev); cudaFree(h->job_slot_dev);
+  if (h->thetas_host) cudaFreeHost(h->thetas_host);
+  if (h->job_slot_host) cudaFreeHost(h->job_slot_host);
+  if (h->mu_host) cudaFreeHost(h->mu_host);
   if (h->results_host) cudaFreeHost(h->results_host);
   cudaFree(h->cw.linv); cudaFree(h->cw.logdet_part); cudaFree(h->cw.info);
   cudaFree(h->fw.gram_part); cudaFree(h->fw.quad_part);
@@ -79,15 +78,55 @@ void vc_free_handle(vc_handle* h) {
   delete h;
 }
 
+// per-JOB buffers (one job = one requested evaluation): result records, mu, the slot it reads, finalize partials
 static void ensure_result_slots(vc_handle* h, int m) {
   if (m <= h->result_slots) return;
-  cudaFree(h->results); cudaFree(h->mu_in);
+  cudaFree(h->results); cudaFree(h->mu_in); cudaFree(h->job_slot_dev); cudaFree(h->fw.gram_part); cudaFree(h->fw.quad_part);
   if (h->results_host) cudaFreeHost(h->results_host);
+  if (h->job_slot_host) cudaFreeHost(h->job_slot_host);
+  if (h->mu_host) cudaFreeHost(h->mu_host);
+  if (h->thetas_host) cudaFreeHost(h->thetas_host);
   h->results = nullptr; h->mu_in = nullptr; h->results_host = nullptr; h->result_slots = 0;
+  h->job_slot_dev = nullptr; h->job_slot_host = nullptr; h->mu_host = nullptr; h->thetas_host = nullptr;
+  h->fw.gram_part = nullptr; h->fw.quad_part = nullptr;
+  const int pm = h->p + 1;
   VC_CUDA_TRY(cudaMalloc(&h->results, (size_t)m * VC_RES_STRIDE * sizeof(double)));
   VC_CUDA_TRY(cudaMalloc(&h->mu_in, (size_t)m * 128 * sizeof(double)));
+  VC_CUDA_TRY(cudaMalloc(&h->job_slot_dev, (size_t)m * sizeof(int)));
+  VC_CUDA_TRY(cudaMalloc(&h->fw.gram_part, (size_t)m * h->fw.blocks * pm * (pm + 1) * sizeof(double)));
+  VC_CUDA_TRY(cudaMalloc(&h->fw.quad_part, (size_t)m * h->fw.blocks * 2 * sizeof(double)));
   VC_CUDA_TRY(cudaMallocHost(&h->results_host, (size_t)m * VC_RES_STRIDE * sizeof(double)));
+  VC_CUDA_TRY(cudaMallocHost(&h->job_slot_host, (size_t)m * sizeof(int)));
+  VC_CUDA_TRY(cudaMallocHost(&h->mu_host, (size_t)m * 128 * sizeof(double)));
+  // one staging entry per distinct theta of a call (never reused within a call: the H2D copies are asynchronous)
+  VC_CUDA_TRY(cudaMallocHost(&h->thetas_host, (size_t)m * sizeof(VcTheta)));
   h->result_slots = m;
+}
+
+// per-SLOT buffers: matrix, border, diagonal-tile inverses, log-det partials, info, theta staging
+static void alloc_slot_buffers(vc_handle* h, int S) {
+  cudaFree(h->M.a); cudaFree(h->M.b); cudaFree(h->cw.linv); cudaFree(h->cw.logdet_part); cudaFree(h->cw.info);
+  cudaFree(h->thetas_dev);
+  h->M.a = h->M.b = h->cw.linv = h->cw.logdet_part = nullptr;
+  h->cw.info = nullptr; h->thetas_dev = nullptr;
+  h->slots = 0;
+  h->factor_valid = false;
+  h->factor_theta.clear();
+  const int64_t np = h->n_pad;
+  const size_t linv_doubles = (size_t)h->M.nt * VC_TILE * VC_TILE;
+  h->M.a_es = h->M.a_doubles;
+  h->M.b_es = h->M.ldb * np;
+  h->M.nbatch = 1;
+  VC_CUDA_TRY(cudaMalloc(&h->M.a, (size_t)S * h->M.a_doubles * sizeof(double)));
+  VC_CUDA_TRY(cudaMalloc(&h->M.b, (size_t)S * h->M.b_es * sizeof(double)));
+  VC_CUDA_TRY(cudaMalloc(&h->cw.linv, (size_t)S * linv_doubles * sizeof(double)));
+  // the diagonal-tile kernel writes only the lower 16x16 blocks of each inverse; the rest stays zero
+  // (on the handle's own stream: a legacy-stream memset is not ordered against non-blocking streams)
+  VC_CUDA_TRY(cudaMemsetAsync(h->cw.linv, 0, (size_t)S * linv_doubles * sizeof(double), h->st_main));
+  VC_CUDA_TRY(cudaMalloc(&h->cw.logdet_part, (size_t)S * h->M.nt * sizeof(double)));
+  VC_CUDA_TRY(cudaMalloc(&h->cw.info, (size_t)S * sizeof(int)));
+  VC_CUDA_TRY(cudaMalloc(&h->thetas_dev, (size_t)S * sizeof(VcTheta)));
+  h->slots = S;
 }
 
 void vc_set_layout(vc_handle* h, const std::vector<int>& r0, const std::vector<int>& ncols, int local_rows) {
@@ -132,7 +171,6 @@ vc_handle* vc_alloc_common(const vc_config* cfg, int64_t n, int d, int p, int q,
     upload_padded(h->x, X, n, np, p, h->st_main);
     upload_padded(h->w, W, n, np, q, h->st_main);
     upload_padded(h->y, y, n, np, 1, h->st_main);
-    ensure_result_slots(h, 64);
     h->M.n = n; h->M.n_pad = np; h->M.nt = (int)(np / VC_TILE);
     h->M.nbt = 1;
     h->M.ldb = VC_BORDER_ROWS;
@@ -155,22 +193,17 @@ vc_handle* vc_alloc_common(const vc_config* cfg, int64_t n, int d, int p, int q,
       std::vector<int> r0, ncols;
       for (int c = 0; c * blk < nt; ++c) { r0.push_back(c * blk); ncols.push_back(std::min(blk, nt - c * blk)); }
       vc_set_layout(h, r0, ncols, nt);
-      VC_CUDA_TRY(cudaMalloc(&h->M.a, (size_t)h->M.a_doubles * sizeof(double)));
-      VC_CUDA_TRY(cudaMalloc(&h->M.b, (size_t)h->M.ldb * np * sizeof(double)));
-      VC_CUDA_TRY(cudaMalloc(&h->cw.linv, (size_t)h->M.nt * VC_TILE * VC_TILE * sizeof(double)));
-      // the diagonal-tile kernel writes only the lower 16x16 blocks of each inverse; the rest stays zero
-      // (on the handle's own stream: a legacy-stream memset is not ordered against non-blocking streams)
-      VC_CUDA_TRY(cudaMemsetAsync(h->cw.linv, 0, (size_t)h->M.nt * VC_TILE * VC_TILE * sizeof(double), h->st_main));
-      VC_CUDA_TRY(cudaMalloc(&h->cw.logdet_part, (size_t)h->M.nt * sizeof(double)));
+      alloc_slot_buffers(h, 1);
+    } else {
+      h->M.nbatch = 1;
+      VC_CUDA_TRY(cudaMalloc(&h->cw.info, sizeof(int)));
     }
-    VC_CUDA_TRY(cudaMalloc(&h->cw.info, sizeof(int)));
     int blocks = (int)(n / 512);
     if (blocks < 1) blocks = 1;
     if (blocks > 148) blocks = 148;
     h->fw.blocks = blocks;
     const int m = p + 1;
-    VC_CUDA_TRY(cudaMalloc(&h->fw.gram_part, (size_t)blocks * m * (m + 1) * sizeof(double)));
-    VC_CUDA_TRY(cudaMalloc(&h->fw.quad_part, (size_t)blocks * 2 * sizeof(double)));
+    ensure_result_slots(h, 64);
     VC_CUDA_TRY(cudaMalloc(&h->gram_dev, (size_t)m * m * sizeof(double)));
     vc_build_init();
     vc_chol_init();
@@ -216,7 +249,6 @@ extern "C" int vc_set_data(vc_handle* h, const double* locs, const double* X, co
     if (y) upload_padded(h->y, y, h->n, h->n_pad, 1, h->st_main);
     h->factor_valid = false;
     h->factor_theta.clear();
-    for (VcLane* L : h->lanes) L->factor_theta.clear();
   } catch (const VcError& e) {
     return vc_fail(h, e.code, e.msg);
   }
@@ -243,96 +275,35 @@ int vc_make_theta(const vc_handle* h, const double* theta, VcTheta* t) {
   return VC_OK;
 }
 
-// how many evaluation lanes a batch may use: one evaluation fills the GPU from n ~ 20k on
-static int lane_cap(const vc_handle* h) {
+// how many evaluation slots a batch may use: one evaluation fills the GPU from n ~ 25k on
+static int slot_cap(const vc_handle* h) {
   if (h->dist) return 1;
-  static const int env_cap = getenv("VC_MAX_LANES") ? atoi(getenv("VC_MAX_LANES")) : 0;   // tuning / debugging
-  if (env_cap >= 1) return std::min(env_cap, 4);
-  if (h->n_pad <= 12288) return 4;
-  if (h->n_pad <= 24576) return 2;
-  return 1;
+  static const int env_cap = getenv("VC_MAX_SLOTS") ? atoi(getenv("VC_MAX_SLOTS")) : 0;   // tuning / debugging
+  if (h->n_pad > 24576) return 1;
+  const double bytes = 8.0 * ((double)h->M.a_doubles + (double)h->M.ldb * h->n_pad + (double)h->M.nt * VC_TILE * VC_TILE);
+  size_t free_b = 0, total_b = 0;
+  cudaMemGetInfo(&free_b, &total_b);
+  const double budget = std::min(24e9, 0.5 * ((double)free_b + (double)h->slots * bytes));
+  int cap = (int)std::max(1.0, std::min(32.0, floor(budget / bytes)));
+  if (env_cap >= 1) cap = std::min(cap, env_cap);
+  return cap;
 }
 
-static void free_lane(VcLane* L) {
-  if (!L) return;
-  cudaFree(L->M.a); cudaFree(L->M.b); vc_chol_free_plans(L->cw);
-  cudaFree(L->cw.linv); cudaFree(L->cw.logdet_part); cudaFree(L->cw.info);
-  cudaFree(L->fw.gram_part); cudaFree(L->fw.quad_part); cudaFree(L->gram_dev);
-  if (L->cw.ev_panel) cudaEventDestroy(L->cw.ev_panel);
-  if (L->cw.ev_update) cudaEventDestroy(L->cw.ev_update);
-  if (L->cw.ev_col) cudaEventDestroy(L->cw.ev_col);
-  if (L->ev_done) cudaEventDestroy(L->ev_done);
-  if (L->st_main) cudaStreamDestroy(L->st_main);
-  if (L->st_panel) cudaStreamDestroy(L->st_panel);
-  delete L;
-}
-
-// A lane joins h->lanes only when every stream, event and buffer of it exists: a half-built lane must
-// never be visible to a later batch (it would launch on null pointers).  Throws VcError on failure.
-static void make_lane(vc_handle* h) {
-  VcLane* L = new VcLane();
-  try {
-    const int64_t np = h->n_pad;
-    int lo = 0, hi = 0;
-    VC_CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-    VC_CUDA_TRY(cudaStreamCreateWithPriority(&L->st_main, cudaStreamNonBlocking, lo));
-    VC_CUDA_TRY(cudaStreamCreateWithPriority(&L->st_panel, cudaStreamNonBlocking, hi));
-    VC_CUDA_TRY(cudaEventCreateWithFlags(&L->cw.ev_panel, cudaEventDisableTiming));
-    VC_CUDA_TRY(cudaEventCreateWithFlags(&L->cw.ev_update, cudaEventDisableTiming));
-    VC_CUDA_TRY(cudaEventCreateWithFlags(&L->cw.ev_col, cudaEventDisableTiming));
-    VC_CUDA_TRY(cudaEventCreateWithFlags(&L->ev_done, cudaEventDisableTiming));
-    L->M = h->M;
-    L->M.a = nullptr; L->M.b = nullptr;
-    L->M.nbt = 1; L->M.ldb = VC_BORDER_ROWS;
-    VC_CUDA_TRY(cudaMalloc(&L->M.a, (size_t)L->M.a_doubles * sizeof(double)));
-    VC_CUDA_TRY(cudaMalloc(&L->M.b, (size_t)L->M.ldb * np * sizeof(double)));
-    L->cw.nb_tiles = h->cw.nb_tiles; L->cw.lookahead = h->cw.lookahead;
-    L->cw.legacy_syrk = h->cw.legacy_syrk; L->cw.legacy_potrf = h->cw.legacy_potrf; L->cw.num_sms = h->cw.num_sms;
-    L->cw.st_main = L->st_main; L->cw.st_panel = L->st_panel;
-    VC_CUDA_TRY(cudaMalloc(&L->cw.linv, (size_t)L->M.nt * VC_TILE * VC_TILE * sizeof(double)));
-    VC_CUDA_TRY(cudaMemsetAsync(L->cw.linv, 0, (size_t)L->M.nt * VC_TILE * VC_TILE * sizeof(double), L->st_main));
-    VC_CUDA_TRY(cudaMalloc(&L->cw.logdet_part, (size_t)L->M.nt * sizeof(double)));
-    VC_CUDA_TRY(cudaMalloc(&L->cw.info, sizeof(int)));
-    const int m = h->p + 1;
-    L->fw.blocks = h->fw.blocks;
-    VC_CUDA_TRY(cudaMalloc(&L->fw.gram_part, (size_t)L->fw.blocks * m * (m + 1) * sizeof(double)));
-    VC_CUDA_TRY(cudaMalloc(&L->fw.quad_part, (size_t)L->fw.blocks * 2 * sizeof(double)));
-    VC_CUDA_TRY(cudaMalloc(&L->gram_dev, (size_t)m * m * sizeof(double)));
-  } catch (...) {
-    free_lane(L);
-    throw;
+// grow the slot buffers to S evaluations (halving on out-of-memory); returns the slots available
+static int ensure_slots(vc_handle* h, int S) {
+  if (S <= h->slots) return h->slots;
+  while (S > h->slots) {
+    try {
+      alloc_slot_buffers(h, S);
+      return h->slots;
+    } catch (const VcError& e) {
+      if (e.code != VC_ERR_OOM) throw;
+      (void)cudaGetLastError();
+      S = std::max(S / 2, 1);
+      if (S <= 1) { alloc_slot_buffers(h, 1); return 1; }
+    }
   }
-  h->lanes.push_back(L);
-}
-
-// enqueue one evaluation on a lane (lane < 0: the handle's own matrix and streams); result record
-// `slot`.  When theta equals the theta of the factor already resident in that lane (optim's probes of
-// the mean parameters in the non-profile objective, vc_post after a fit), only the O(n p) finalize runs.
-static void enqueue_eval(vc_handle* h, int lane, const VcTheta& th, const double* theta, int mu_mode,
-                         int slot, bool timed) {
-  VcLane* L = lane >= 0 ? h->lanes[lane] : nullptr;
-  VcMatrix& M = L ? L->M : h->M;
-  VcCholWork& cw = L ? L->cw : h->cw;
-  VcFinalWork& fw = L ? L->fw : h->fw;
-  std::vector<double>& ft = L ? L->factor_theta : h->factor_theta;
-  cudaStream_t st = L ? L->st_main : h->st_main;
-  const size_t nth = (size_t)2 * h->q + 1;
-  const bool cached = ft.size() == nth && memcmp(ft.data(), theta, nth * sizeof(double)) == 0;
-  if (timed) VC_CUDA_TRY(cudaEventRecord(h->ev[0], st));
-  if (!cached) {
-    vc_launch_build(M, th, h->d, h->locs, h->w, st, &h->launches);
-    vc_launch_border(M, h->p, h->x, h->y, st, &h->launches);
-  }
-  if (timed) VC_CUDA_TRY(cudaEventRecord(h->ev[1], st));
-  if (!cached) {
-    M.nbt = 1;
-    vc_chol_factor(M, cw, &h->launches);
-    ft.assign(theta, theta + nth);
-  }
-  if (timed) VC_CUDA_TRY(cudaEventRecord(h->ev[2], st));
-  vc_launch_finalize(M, h->p, mu_mode, h->mu_in + (size_t)slot * 128, cw.logdet_part, cw.info, fw,
-                     h->results + (size_t)slot * VC_RES_STRIDE, st, &h->launches, L ? L->gram_dev : h->gram_dev);
-  if (timed) VC_CUDA_TRY(cudaEventRecord(h->ev[3], st));
+  return h->slots;
 }
 
 extern "C" int vc_n2ll_batch(vc_handle* h, int32_t m, const double* thetas, int32_t mu_mode,
@@ -359,46 +330,97 @@ extern "C" int vc_n2ll_batch(vc_handle* h, int32_t m, const double* thetas, int3
     VC_CUDA_TRY(cudaSetDevice(h->device));
     ensure_result_slots(h, m);
     std::vector<int> status(m, VC_OK);
-    if (mu_mode == VC_MU_FIXED)
-      VC_CUDA_TRY(cudaMemcpy2DAsync(h->mu_in, 128 * sizeof(double), mus_in, h->p * sizeof(double),
-                                    h->p * sizeof(double), m, cudaMemcpyHostToDevice, h->st_main));
-    // lanes: evaluation e runs on lane (m - 1 - e) % nl, so the LAST one lands on the handle's own
-    // matrix (vc_get_chol / vc_get_whitened / vc_post refer to it)
-    int nl = std::min(m, lane_cap(h));
-    while ((int)h->lanes.size() < nl - 1) {
-      try {
-        make_lane(h);
-      } catch (const VcError& e) {
-        if (e.code != VC_ERR_OOM) throw;
-        (void)cudaGetLastError();                 // out of device memory: run the batch on the lanes that exist
-        nl = (int)h->lanes.size() + 1;
-      }
-    }
-    if (nl > 1) {
-      if (!h->ev_inputs) VC_CUDA_TRY(cudaEventCreateWithFlags(&h->ev_inputs, cudaEventDisableTiming));
-      VC_CUDA_TRY(cudaEventRecord(h->ev_inputs, h->st_main));   // inputs / mu staged on st_main
-      for (int l = 0; l < nl - 1; ++l) VC_CUDA_TRY(cudaStreamWaitEvent(h->lanes[l]->st_main, h->ev_inputs, 0));
-    }
+    // ---- jobs with a valid theta; distinct thetas (optim's probes of the mean parameters in the non-profile
+    // objective repeat theta: they share one factorisation and differ only in the O(n p) finalize) ----
+    std::vector<int> uniq_of(m, -1);            // evaluation -> index into `uniq`
+    std::vector<int> uniq;                      // first evaluation of every distinct theta
     for (int e = 0; e < m; ++e) {
       VcTheta th;
-      if (vc_make_theta(h, thetas + (size_t)e * nth, &th) != VC_OK) {
-        status[e] = VC_ERR_INVALID;
-        continue;
+      if (vc_make_theta(h, thetas + (size_t)e * nth, &th) != VC_OK) { status[e] = VC_ERR_INVALID; continue; }
+      int u = -1;
+      for (size_t k = 0; k < uniq.size() && u < 0; ++k)
+        if (memcmp(thetas + (size_t)uniq[k] * nth, thetas + (size_t)e * nth, nth * sizeof(double)) == 0) u = (int)k;
+      if (u < 0) { u = (int)uniq.size(); uniq.push_back(e); }
+      uniq_of[e] = u;
+    }
+    int last_valid = -1;
+    for (int e = m - 1; e >= 0 && last_valid < 0; --e) if (status[e] == VC_OK) last_valid = e;
+    const int nu = (int)uniq.size();
+    // the resident factor of slot 0 (a repeated theta, vc_post after a fit) is reused when the whole call is about it
+    const bool cached = nu == 1 && h->factor_theta.size() == (size_t)nth &&
+                        memcmp(h->factor_theta.data(), thetas + (size_t)uniq[0] * nth, nth * sizeof(double)) == 0;
+    int S = 1;
+    if (nu > 1) S = ensure_slots(h, std::min(nu, slot_cap(h)));
+    // order of the distinct thetas: the theta of the last valid evaluation goes last, so that it lands in slot 0
+    // of the last group (vc_get_chol / vc_get_whitened / vc_post refer to slot 0)
+    std::vector<int> order;
+    const int u_last = last_valid >= 0 ? uniq_of[last_valid] : -1;
+    for (int u = 0; u < nu; ++u) if (u != u_last) order.push_back(u);
+    if (u_last >= 0) order.push_back(u_last);
+    std::vector<int> rec_of(m, -1);             // evaluation -> result record
+    int rec_base = 0;
+    cudaStream_t st = h->st_main;
+    for (int g0 = 0; g0 < nu; g0 += S) {
+      const int gsz = std::min(S, nu - g0);
+      const bool last_group = g0 + gsz >= nu;
+      // slot i of this group holds distinct theta order[g0 + gsz - 1 - i]: the group's last theta sits in slot 0
+      std::vector<int> slot_of_u(nu, -1);
+      for (int i = 0; i < gsz; ++i) {
+        const int u = order[g0 + gsz - 1 - i];
+        slot_of_u[u] = i;
+        vc_make_theta(h, thetas + (size_t)uniq[u] * nth, &h->thetas_host[g0 + i]);
       }
-      const int lane = (m - 1 - e) % nl;              // 0 = the handle itself
-      enqueue_eval(h, lane - 1, th, thetas + (size_t)e * nth, mu_mode, e, e == m - 1);
+      // jobs of this group, in evaluation order
+      int njobs = 0;
+      for (int e = 0; e < m; ++e) {
+        if (status[e] != VC_OK || slot_of_u[uniq_of[e]] < 0) continue;
+        const int r = rec_base + njobs;
+        rec_of[e] = r;
+        h->job_slot_host[r] = slot_of_u[uniq_of[e]];
+        if (mu_mode == VC_MU_FIXED)
+          memcpy(h->mu_host + (size_t)r * 128, mus_in + (size_t)e * h->p, h->p * sizeof(double));
+        ++njobs;
+      }
+      if (njobs == 0) continue;
+      VC_CUDA_TRY(cudaMemcpyAsync(h->job_slot_dev + rec_base, h->job_slot_host + rec_base, njobs * sizeof(int),
+                                  cudaMemcpyHostToDevice, st));
+      if (mu_mode == VC_MU_FIXED)
+        VC_CUDA_TRY(cudaMemcpyAsync(h->mu_in + (size_t)rec_base * 128, h->mu_host + (size_t)rec_base * 128,
+                                    (size_t)njobs * 128 * sizeof(double), cudaMemcpyHostToDevice, st));
+      VcMatrix M = h->M;
+      M.nbatch = gsz;
+      M.nbt = 1;
+      const bool timed = last_group;
+      if (timed) VC_CUDA_TRY(cudaEventRecord(h->ev[0], st));
+      if (!cached) {
+        if (gsz > 1) {
+          VC_CUDA_TRY(cudaMemcpyAsync(h->thetas_dev, h->thetas_host + g0, gsz * sizeof(VcTheta), cudaMemcpyHostToDevice, st));
+          vc_launch_build(M, h->thetas_host[g0], h->d, h->locs, h->w, st, &h->launches, h->thetas_dev);
+        } else {
+          vc_launch_build(M, h->thetas_host[g0], h->d, h->locs, h->w, st, &h->launches);   // theta by value: no copy
+        }
+        vc_launch_border(M, h->p, h->x, h->y, st, &h->launches);
+      }
+      if (timed) VC_CUDA_TRY(cudaEventRecord(h->ev[1], st));
+      if (!cached) {
+        h->factor_theta.clear();
+        vc_chol_factor(M, h->cw, &h->launches);
+      }
+      if (timed) VC_CUDA_TRY(cudaEventRecord(h->ev[2], st));
+      vc_launch_finalize(M, h->p, mu_mode, h->mu_in + (size_t)rec_base * 128, h->cw.logdet_part, h->cw.info, h->fw,
+                         h->results + (size_t)rec_base * VC_RES_STRIDE, st, &h->launches, h->gram_dev,
+                         njobs, h->job_slot_dev + rec_base);
+      if (timed) VC_CUDA_TRY(cudaEventRecord(h->ev[3], st));
+      rec_base += njobs;
     }
-    for (int l = 0; l < nl - 1; ++l) {
-      VC_CUDA_TRY(cudaEventRecord(h->lanes[l]->ev_done, h->lanes[l]->st_main));
-      VC_CUDA_TRY(cudaStreamWaitEvent(h->st_main, h->lanes[l]->ev_done, 0));
-    }
-    VC_CUDA_TRY(cudaMemcpyAsync(h->results_host, h->results, (size_t)m * VC_RES_STRIDE * sizeof(double),
-                                cudaMemcpyDeviceToHost, h->st_main));
-    VC_CUDA_TRY(cudaStreamSynchronize(h->st_main));
+    if (rec_base > 0)
+      VC_CUDA_TRY(cudaMemcpyAsync(h->results_host, h->results, (size_t)rec_base * VC_RES_STRIDE * sizeof(double),
+                                  cudaMemcpyDeviceToHost, st));
+    VC_CUDA_TRY(cudaStreamSynchronize(st));
     VC_CUDA_TRY(cudaGetLastError());
     for (int e = 0; e < m; ++e) {
-      const double* r = h->results_host + (size_t)e * VC_RES_STRIDE;
       if (status[e] == VC_OK) {
+        const double* r = h->results_host + (size_t)rec_of[e] * VC_RES_STRIDE;
         const int info = (int)r[VC_RES_INFO];
         if (info != 0) { status[e] = VC_ERR_NOT_PD; h->last_info = info; }
         out_n2ll[e] = r[VC_RES_N2LL];
@@ -410,14 +432,17 @@ extern "C" int vc_n2ll_batch(vc_handle* h, int32_t m, const double* thetas, int3
       if (out_status) out_status[e] = status[e];
       if (status[e] != VC_OK && first == VC_OK) first = status[e];
     }
-    if (status[m - 1] == VC_OK || status[m - 1] == VC_ERR_NOT_PD) {
+    if (last_valid >= 0) {
       float b = 0, c = 0, f = 0;
       cudaEventElapsedTime(&b, h->ev[0], h->ev[1]);
       cudaEventElapsedTime(&c, h->ev[1], h->ev[2]);
       cudaEventElapsedTime(&f, h->ev[2], h->ev[3]);
       h->last_timing = {b, c, f, b + c + f};
+      // slot 0 now holds the factor of the last valid evaluation
+      h->factor_theta.assign(thetas + (size_t)last_valid * nth, thetas + (size_t)(last_valid + 1) * nth);
+      h->factor_valid = (status[last_valid] == VC_OK);
+      h->last_rec = rec_of[last_valid];
     }
-    h->factor_valid = (status[m - 1] == VC_OK);
     if (first == VC_ERR_NOT_PD) {
       char buf[128];
       snprintf(buf, sizeof(buf), "the leading minor of order %d is not positive", h->last_info);
@@ -427,7 +452,6 @@ extern "C" int vc_n2ll_batch(vc_handle* h, int32_t m, const double* thetas, int3
     }
   } catch (const VcError& e) {
     h->factor_theta.clear();
-    for (VcLane* L : h->lanes) L->factor_theta.clear();
     h->factor_valid = false;
     return vc_fail(h, e.code, e.msg);
   }
@@ -442,8 +466,9 @@ extern "C" int vc_n2ll(vc_handle* h, const double* theta, int32_t mu_mode, const
   h->last_info = 0;
   int rc = vc_n2ll_batch(h, 1, theta, mu_mode, mu_in, n2ll, mu_out, &status);
   if (rc == VC_OK || rc == VC_ERR_NOT_PD) {
-    if (logdet) *logdet = h->results_host[VC_RES_LOGDET];
-    if (quad) *quad = h->results_host[VC_RES_QUAD];
+    const double* r = h->results_host + (size_t)h->last_rec * VC_RES_STRIDE;
+    if (logdet) *logdet = r[VC_RES_LOGDET];
+    if (quad) *quad = r[VC_RES_QUAD];
   }
   return rc;
 }

@@ -13,6 +13,7 @@
 // padded matrix factors to [L 0; 0 I].
 #include "vc_common.cuh"
 #include "vc_math.cuh"
+#include <algorithm>
 
 namespace {
 
@@ -34,8 +35,20 @@ struct BuildArgs {
   const int* tiles;     // optional list of packed (I | J << 16) global tiles (distributed build)
   const VcColBlock* cb; // block-column storage of the OUTPUT (lower tiles); nullptr = dense `out` with `ld` (FULL)
   int blk, pr, pc;      // tiles per storage block; process grid of a block-cyclic output (1 x 1 = plain)
-  VcTheta th;
+  int64_t out_es;       // batched build: slot e = blockIdx.y writes out + e * out_es with the parameters th_dev[e]
+  const VcTheta* th_dev;
+  VcTheta th;           // model (cov / taper / distance / q) and, when th_dev == nullptr, the parameters
 };
+// covariance parameters of this CTA's evaluation slot: by-value block (single) or the device array (batched)
+__device__ __forceinline__ double th_inv_range(const BuildArgs& p, int k) {
+  return p.th_dev ? p.th_dev[blockIdx.y].inv_range[k] : p.th.inv_range[k];
+}
+__device__ __forceinline__ double th_sill(const BuildArgs& p, int k) {
+  return p.th_dev ? p.th_dev[blockIdx.y].sill[k] : p.th.sill[k];
+}
+__device__ __forceinline__ double th_tau2(const BuildArgs& p) {
+  return p.th_dev ? p.th_dev[blockIdx.y].tau2 : p.th.tau2;
+}
 
 // shared layout: tab[64] | colX[d][128] | colW[q][128] | rowX[d][128] | rowA[q][128] (rowA = W rows)
 template <int COV, bool REG, bool FULL>
@@ -87,8 +100,9 @@ __global__ void __launch_bounds__(BUILD_THREADS) k_build(BuildArgs p) {
   if (!FULL) {
     const int lI = p.pr > 1 ? ((I / p.blk) / p.pr) * p.blk + I % p.blk : I;
     const int lJ = p.pc > 1 ? ((J / p.blk) / p.pc) * p.blk + J % p.blk : J;
-    otile = vc_tile_ptr(p.out, p.cb, p.blk, lI, lJ, old_) + r0;
+    otile = vc_tile_ptr(p.out + blockIdx.y * p.out_es, p.cb, p.blk, lI, lJ, old_) + r0;
   }
+  const double tau2 = th_tau2(p);
   const int method = p.th.dist_method;
   const double mink = p.th.mink_p;
 
@@ -99,7 +113,7 @@ __global__ void __launch_bounds__(BUILD_THREADS) k_build(BuildArgs p) {
       if (c < d) { xi0[c] = rowX[c * TILE + r0]; xi1[c] = rowX[c * TILE + r0 + 1]; }
 #pragma unroll
     for (int k = 0; k < RQ; ++k)
-      if (k < q) { ai0[k] = rowA[k * TILE + r0]; ai1[k] = rowA[k * TILE + r0 + 1]; ir[k] = p.th.inv_range[k]; sk[k] = p.th.sill[k]; }
+      if (k < q) { ai0[k] = rowA[k * TILE + r0]; ai1[k] = rowA[k * TILE + r0 + 1]; ir[k] = th_inv_range(p, k); sk[k] = th_sill(p, k); }
   }
 
   for (int cc = 0; cc < 32; ++cc) {
@@ -144,8 +158,8 @@ __global__ void __launch_bounds__(BUILD_THREADS) k_build(BuildArgs p) {
     } else {
       for (int k = 0; k < q; ++k) {
         const double wj = colW[k * TILE + j];
-        const double irk = p.th.inv_range[k];
-        const double sk_ = p.th.sill[k];
+        const double irk = th_inv_range(p, k);
+        const double sk_ = th_sill(p, k);
         v0 = fma(rowA[k * TILE + r0] * wj, sk_ * vc_cov_shape<COV>(h0 * irk, tab), v0);
         v1 = fma(rowA[k * TILE + r0 + 1] * wj, sk_ * vc_cov_shape<COV>(h1 * irk, tab), v1);
       }
@@ -154,8 +168,8 @@ __global__ void __launch_bounds__(BUILD_THREADS) k_build(BuildArgs p) {
       v0 *= vc_taper(p.th.taper_id, h0, p.th.inv_delta);
       v1 *= vc_taper(p.th.taper_id, h1, p.th.inv_delta);
     }
-    if (gi0 == gj) v0 += (gj < p.n) ? p.th.tau2 : 1.0;
-    if (gi0 + 1 == gj) v1 += (gj < p.n) ? p.th.tau2 : 1.0;
+    if (gi0 == gj) v0 += (gj < p.n) ? tau2 : 1.0;
+    if (gi0 + 1 == gj) v1 += (gj < p.n) ? tau2 : 1.0;
     if (FULL) {
       if (gj < p.n) {
         if (gi0 < p.n) p.out[gi0 + gj * p.ld] = v0;
@@ -207,13 +221,14 @@ __global__ void __launch_bounds__(BUILD_THREADS, 3) k_build_fast(BuildArgs p) {
   for (int k = 0; k < Q; ++k) {
     const double2 v = *reinterpret_cast<const double2*>(p.w + (int64_t)k * p.n_pad + gi0);
     wi0[k] = v.x; wi1[k] = v.y;
-    ir[k] = p.th.inv_range[k];
-    sk[k] = p.th.sill[k];
+    ir[k] = th_inv_range(p, k);
+    sk[k] = th_sill(p, k);
   }
+  const double tau2 = th_tau2(p);
   const int lI = p.pr > 1 ? ((I / p.blk) / p.pr) * p.blk + I % p.blk : I;
   const int lJ = p.pc > 1 ? ((J / p.blk) / p.pc) * p.blk + J % p.blk : J;
   int64_t old_;
-  double* out = vc_tile_ptr(p.out, p.cb, p.blk, lI, lJ, old_) + r0;
+  double* out = vc_tile_ptr(p.out + blockIdx.y * p.out_es, p.cb, p.blk, lI, lJ, old_) + r0;
   const int taper_id = p.th.taper_id;
   const double inv_delta = p.th.inv_delta;
   __syncthreads();
@@ -241,14 +256,14 @@ __global__ void __launch_bounds__(BUILD_THREADS, 3) k_build_fast(BuildArgs p) {
       v0 *= vc_taper(taper_id, h0, inv_delta);
       v1 *= vc_taper(taper_id, h1, inv_delta);
     }
-    if (gi0 == gj) v0 += (gj < p.n) ? p.th.tau2 : 1.0;
-    if (gi0 + 1 == gj) v1 += (gj < p.n) ? p.th.tau2 : 1.0;
+    if (gi0 == gj) v0 += (gj < p.n) ? tau2 : 1.0;
+    if (gi0 + 1 == gj) v1 += (gj < p.n) ? tau2 : 1.0;
     *reinterpret_cast<double2*>(out + (int64_t)j * old_) = make_double2(v0, v1);
   }
 }
 
 template <int COV, int D>
-bool launch_fast_q(const BuildArgs& a, unsigned grid, cudaStream_t st) {
+bool launch_fast_q(const BuildArgs& a, dim3 grid, cudaStream_t st) {
   switch (a.th.q) {
     case 1: k_build_fast<COV, D, 1><<<grid, BUILD_THREADS, 0, st>>>(a); return true;
     case 2: k_build_fast<COV, D, 2><<<grid, BUILD_THREADS, 0, st>>>(a); return true;
@@ -258,7 +273,7 @@ bool launch_fast_q(const BuildArgs& a, unsigned grid, cudaStream_t st) {
   }
 }
 template <int COV>
-bool launch_fast_d(const BuildArgs& a, unsigned grid, cudaStream_t st) {
+bool launch_fast_d(const BuildArgs& a, dim3 grid, cudaStream_t st) {
   switch (a.d) {
     case 1: return launch_fast_q<COV, 1>(a, grid, st);
     case 2: return launch_fast_q<COV, 2>(a, grid, st);
@@ -267,7 +282,7 @@ bool launch_fast_d(const BuildArgs& a, unsigned grid, cudaStream_t st) {
   }
 }
 // exp / Matern with Euclidean distances, d <= 3, q <= 4: the common case of the reference's API
-bool launch_fast(const BuildArgs& a, unsigned grid, cudaStream_t st) {
+bool launch_fast(const BuildArgs& a, dim3 grid, cudaStream_t st) {
   if (a.th.dist_method != VC_DIST_EUCLIDEAN) return false;
   switch (a.th.cov_id) {
     case VC_COV_EXP: return launch_fast_d<0>(a, grid, st);
@@ -278,12 +293,12 @@ bool launch_fast(const BuildArgs& a, unsigned grid, cudaStream_t st) {
 }
 
 template <bool FULL>
-void launch_build_t(const BuildArgs& a, cudaStream_t st, unsigned grid_override = 0) {
+void launch_build_t(const BuildArgs& a, cudaStream_t st, unsigned grid_override = 0, int nbatch = 1) {
   const int d = a.d, q = a.th.q;
   const bool reg = (d <= RD && q <= RQ);
   const size_t smem = (VC_EXP_TABLE_SIZE + 2 * (size_t)(d + q) * TILE) * sizeof(double);
-  const unsigned grid = grid_override ? grid_override
-                        : FULL ? (unsigned)a.nt * a.nt : (unsigned)((int64_t)a.nt * (a.nt + 1) / 2);
+  const dim3 grid(grid_override ? grid_override
+                  : FULL ? (unsigned)a.nt * a.nt : (unsigned)((int64_t)a.nt * (a.nt + 1) / 2), (unsigned)std::max(nbatch, 1));
   if (!FULL && launch_fast(a, grid, st)) return;
 #define VC_BUILD_CASE(C)                                                               \
   case C:                                                                              \
@@ -301,7 +316,8 @@ void launch_build_t(const BuildArgs& a, cudaStream_t st, unsigned grid_override 
 
 // border tile 0: B^T[c, j] = X[j, c] (c < p), y[j] (c == p), 0 otherwise
 __global__ void k_border(double* b, int64_t ldb, int64_t n_pad, int p, const double* __restrict__ x,
-                         const double* __restrict__ y) {
+                         const double* __restrict__ y, int64_t b_es) {
+  b += blockIdx.y * b_es;
   const int64_t j = (int64_t)blockIdx.x * 2 + (threadIdx.x >> 7);
   const int c = threadIdx.x & 127;
   if (j >= n_pad) return;
@@ -326,11 +342,12 @@ void vc_build_init() {
 }
 
 void vc_launch_build(const VcMatrix& M, const VcTheta& th, int d, const double* locs_pad,
-                     const double* w_pad, cudaStream_t st, int64_t* launches) {
+                     const double* w_pad, cudaStream_t st, int64_t* launches, const VcTheta* th_dev) {
   BuildArgs a{};
   a.out = M.a; a.cb = M.cb; a.blk = M.blk; a.pr = 1; a.pc = 1; a.n = M.n; a.n_pad = M.n_pad; a.nt = M.nt; a.d = d;
   a.locs = locs_pad; a.w = w_pad; a.th = th;
-  launch_build_t<false>(a, st);
+  a.th_dev = th_dev; a.out_es = M.a_es;
+  launch_build_t<false>(a, st, 0, th_dev ? M.nbatch : 1);
   ++*launches;
 }
 
@@ -382,6 +399,6 @@ void vc_launch_sigma_full(double* out, int64_t n, int64_t n_pad, const VcTheta& 
 
 void vc_launch_border(const VcMatrix& M, int p, const double* x_pad, const double* y_pad,
                       cudaStream_t st, int64_t* launches) {
-  k_border<<<(unsigned)((M.n_pad + 1) / 2), 256, 0, st>>>(M.b, M.ldb, M.n_pad, p, x_pad, y_pad);
+  k_border<<<dim3((unsigned)((M.n_pad + 1) / 2), (unsigned)std::max(M.nbatch, 1)), 256, 0, st>>>(M.b, M.ldb, M.n_pad, p, x_pad, y_pad, M.b_es);
   ++*launches;
 }

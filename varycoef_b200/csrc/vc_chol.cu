@@ -101,26 +101,27 @@ __device__ __forceinline__ int loc_tile(const GemmArgs& p, int t, int P) {
   return P > 1 ? ((t / p.blk) / P) * p.blk + t % p.blk : t;
 }
 // pointer to element (0, col) of row tile I in the (local) matrix / border; col in LOCAL elements
-__device__ __forceinline__ double* row_tile_ptr(const GemmArgs& p, int I, int64_t col, int64_t& ld) {
+// (slot e of a batched launch: the matrix / border of evaluation e)
+__device__ __forceinline__ double* row_tile_ptr(const GemmArgs& p, int e, int I, int64_t col, int64_t& ld) {
   if (I < p.nt) {
-    double* t = vc_tile_ptr(p.a, p.cb, p.blk, loc_tile(p, I, p.pr), (int)(col >> 7), ld);
+    double* t = vc_tile_ptr(p.a + e * p.a_es, p.cb, p.blk, loc_tile(p, I, p.pr), (int)(col >> 7), ld);
     return t + (col & (TILE - 1)) * ld;
   }
   ld = p.ldb;
-  return p.b + (int64_t)(I - p.nt) * TILE + col * p.ldb;
+  return p.b + e * p.b_es + (int64_t)(I - p.nt) * TILE + col * p.ldb;
 }
 // C tile (I, J), J a global column tile
-__device__ __forceinline__ double* c_tile_ptr(const GemmArgs& p, int I, int J, int64_t& ld) {
-  return row_tile_ptr(p, I, (int64_t)loc_tile(p, J, p.pc) * TILE, ld);
+__device__ __forceinline__ double* c_tile_ptr(const GemmArgs& p, int e, int I, int J, int64_t& ld) {
+  return row_tile_ptr(p, e, I, (int64_t)loc_tile(p, J, p.pc) * TILE, ld);
 }
 // operand row tile I, panel column kcol: from a gathered panel buffer, or from the matrix itself
-__device__ __forceinline__ const double* op_ptr(const GemmArgs& p, const VcOpSrc& s, int I, int kcol,
+__device__ __forceinline__ const double* op_ptr(const GemmArgs& p, const VcOpSrc& s, int e, int I, int kcol,
                                                 int64_t& ld) {
   if (s.pnl) {
     ld = s.ld;
     return s.pnl + (int64_t)(I - s.tile0) * s.tile_stride + (int64_t)(s.col0 + kcol) * s.ld;
   }
-  return row_tile_ptr(p, I, (int64_t)p.k0 + kcol, ld);
+  return row_tile_ptr(p, e, I, (int64_t)p.k0 + kcol, ld);
 }
 
 // one pipeline stage of a warp: 4 k4 steps of 12 fragment loads + 32 DMMA.
@@ -193,14 +194,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_trsm_panel(GemmArgs p) {
   const int wm = warp & 1, wn = warp >> 1;
   const int g = lane >> 2, tig = lane & 3;
   int64_t ld;
-  double* Ct = c_tile_ptr(p, I, p.jt, ld);
+  const int e = blockIdx.y;
+  double* Ct = c_tile_ptr(p, e, I, p.jt, ld);
   double acc[8][4][2];
 #pragma unroll
   for (int i = 0; i < 8; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
   // the B operand element (n, k) is Linv[n + 128 k]
-  gemm_mainloop(Ct, ld, p.linv, TILE, TILE, acc, smem);
+  gemm_mainloop(Ct, ld, p.linv + e * p.linv_es, TILE, TILE, acc, smem);
   double* cbase = Ct + (wm * 64 + g) + (int64_t)(wn * 32 + 2 * tig) * ld;
 #pragma unroll
   for (int i = 0; i < 8; ++i)
@@ -222,9 +224,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_syrk_tiles(GemmArgs p) {
   const int wm = warp & 1, wn = warp >> 1;
   const int g = lane >> 2, tig = lane & 3;
   int64_t ldc, ldpi, ldpj;
-  double* Ct = c_tile_ptr(p, I, J, ldc);
-  const double* Pi = op_ptr(p, p.src_a, I, 0, ldpi);
-  const double* Pj = op_ptr(p, p.src_b, J, 0, ldpj);
+  const int e = blockIdx.y;
+  double* Ct = c_tile_ptr(p, e, I, J, ldc);
+  const double* Pi = op_ptr(p, p.src_a, e, I, 0, ldpi);
+  const double* Pj = op_ptr(p, p.src_b, e, J, 0, ldpj);
   double* cbase = Ct + (wm * 64 + g) + (int64_t)(wn * 32 + 2 * tig) * ldc;
   double acc[8][4][2];
 #pragma unroll
@@ -312,13 +315,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_strip(GemmArgs p) {
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 2; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-  // C(I, J) -= P_I P_J^T on rows [32 s, 32 s + 32) of the tile
-  const int packed = p.tiles[t];
+  // C(I, J) -= P_I P_J^T on rows [32 s, 32 s + 32) of the tile; linear tile index lin_first + t over (slot, tile)
+  const int lin = p.lin_first + t;
+  const int e = lin / p.ntiles;
+  const int packed = p.tiles[lin - e * p.ntiles];
   const int I = packed & 0xffff, J = packed >> 16;
   int64_t ldc, ldpi, ldpj;
-  double* Ct = c_tile_ptr(p, I, J, ldc) + STRIP * s;
-  const double* Pi = op_ptr(p, p.src_a, I, 0, ldpi) + STRIP * s;
-  const double* Pj = op_ptr(p, p.src_b, J, 0, ldpj);
+  double* Ct = c_tile_ptr(p, e, I, J, ldc) + STRIP * s;
+  const double* Pi = op_ptr(p, p.src_a, e, I, 0, ldpi) + STRIP * s;
+  const double* Pj = op_ptr(p, p.src_b, e, J, 0, ldpj);
   strip_mainloop(Pi, ldpi, Pj, ldpj, p.K, acc, smem);
   double* cbase = Ct + g + (int64_t)(warp * 16 + 2 * tig) * ldc;
 #pragma unroll
@@ -355,22 +360,27 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_syrk_ws(GemmArgs p) {
   }
   __syncthreads();
   const int nk = p.K / KC;
+  // linear index over (evaluation slot, tile of the list); lin_stop > 0 cuts the walk short (the launcher
+  // hands the last few indices to the strip kernel)
+  const int total = p.lin_stop > 0 ? p.lin_stop : p.ntiles * p.nbatch;
 
   if (warp == 8) {
     // ===== producer =====
     unsigned it = 0;
     const int col = lane & 15, opnd = lane >> 4;
-    for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
-      const int packed = p.tiles[t];
+    for (int t = blockIdx.x; t < total; t += gridDim.x) {
+      const int e = t / p.ntiles;
+      const int packed = p.tiles[t - e * p.ntiles];
       const int I = packed & 0xffff, J = packed >> 16;
       int64_t ldsrc;
-      const double* src = opnd == 0 ? op_ptr(p, p.src_a, I, col, ldsrc) : op_ptr(p, p.src_b, J, col, ldsrc);
+      const double* src = opnd == 0 ? op_ptr(p, p.src_a, e, I, col, ldsrc) : op_ptr(p, p.src_b, e, J, col, ldsrc);
       // pull the NEXT tile's C into L2 while this tile computes (its loads then hit L2)
       const int tn = t + gridDim.x;
-      if (tn < p.ntiles) {
-        const int pk = p.tiles[tn];
+      if (tn < total) {
+        const int en = tn / p.ntiles;
+        const int pk = p.tiles[tn - en * p.ntiles];
         int64_t ldn;
-        const double* cn = c_tile_ptr(p, pk & 0xffff, pk >> 16, ldn);
+        const double* cn = c_tile_ptr(p, en, pk & 0xffff, pk >> 16, ldn);
 #pragma unroll
         for (int c = 0; c < 4; ++c) bulk_prefetch_l2(cn + (int64_t)(lane * 4 + c) * ldn, TILE * 8);
       }
@@ -390,15 +400,16 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_syrk_ws(GemmArgs p) {
     const int wm = warp & 1, wn = warp >> 1;
     const int g = lane >> 2, tig = lane & 3;
     unsigned it = 0;
-    int packed_next = (blockIdx.x < (unsigned)p.ntiles) ? p.tiles[blockIdx.x] : 0;
-    for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
+    int packed_next = ((int)blockIdx.x < total) ? p.tiles[blockIdx.x % p.ntiles] : 0;
+    for (int t = blockIdx.x; t < total; t += gridDim.x) {
       const int packed = packed_next;
+      const int e = t / p.ntiles;
       // the next tile's index is fetched a whole tile ahead: its ~1 us global-load latency would
       // otherwise sit on the critical path of every tile boundary
-      if (t + (int)gridDim.x < p.ntiles) packed_next = p.tiles[t + gridDim.x];
+      if (t + (int)gridDim.x < total) packed_next = p.tiles[(t + gridDim.x) % p.ntiles];
       const int I = packed & 0xffff, J = packed >> 16;
       int64_t ldc;
-      double* Ct = c_tile_ptr(p, I, J, ldc);
+      double* Ct = c_tile_ptr(p, e, I, J, ldc);
       double* cbase = Ct + (wm * 64 + g) + (int64_t)(wn * 32 + 2 * tig) * ldc;
       double acc[8][4][2];
 #pragma unroll
@@ -445,8 +456,8 @@ constexpr int POTRF_THREADS = 256;
 constexpr int POTRF_SMEM = (TILE * (TILE + 1) + TILE) * (int)sizeof(double);
 
 __global__ void __launch_bounds__(POTRF_THREADS, 1)
-k_potrf128(double* __restrict__ At, int64_t lda, int jt, double* __restrict__ linv_all,
-           double* __restrict__ logdet_part, int* __restrict__ info) {
+k_potrf128(double* At, int64_t lda, int jt, double* linv_all, double* logdet_part, int* info, VcPotrfBatch bat) {
+  At += blockIdx.x * bat.a_es; linv_all += blockIdx.x * bat.linv_es; logdet_part += blockIdx.x * bat.nt; info += blockIdx.x;
   extern __shared__ __align__(16) double M[];
   double* sdiag = M + TILE * (TILE + 1);
   const int tid = threadIdx.x;
@@ -540,8 +551,8 @@ __device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync
 
 template <bool FACTOR>   // FACTOR = false: the tile already holds L; only invert it (vc_gls_chol)
 __global__ void __launch_bounds__(POTRF_THREADS, 1)
-k_potrf128b(double* __restrict__ At, int64_t lda, int jt, double* __restrict__ linv_all,
-            double* __restrict__ logdet_part, int* __restrict__ info) {
+k_potrf128b(double* At, int64_t lda, int jt, double* linv_all, double* logdet_part, int* info, VcPotrfBatch bat) {
+  At += blockIdx.x * bat.a_es; linv_all += blockIdx.x * bat.linv_es; logdet_part += blockIdx.x * bat.nt; info += blockIdx.x;
   extern __shared__ __align__(16) double M[];
   double* sdiag = M + (TILE + 1) * PLD;
   double* scratch = sdiag + TILE;
@@ -1045,8 +1056,8 @@ __device__ __forceinline__ void potrf_store_X_rows(const double* M, double* linv
 
 template <bool FACTOR>
 __global__ void __launch_bounds__(POTRF_THREADS, 1)
-k_potrf128c(double* __restrict__ At, int64_t lda, int jt, double* __restrict__ linv_all,
-            double* __restrict__ logdet_part, int* __restrict__ info) {
+k_potrf128c(double* At, int64_t lda, int jt, double* linv_all, double* logdet_part, int* info, VcPotrfBatch bat) {
+  At += blockIdx.x * bat.a_es; linv_all += blockIdx.x * bat.linv_es; logdet_part += blockIdx.x * bat.nt; info += blockIdx.x;
   extern __shared__ __align__(16) double M[];
   double* sdiag = M + (TILE + 1) * PLD;
   double* scratch = sdiag + TILE;
@@ -1159,7 +1170,7 @@ __global__ void __launch_bounds__(256) k_pack_tiles(GemmArgs p, const int* __res
                                                     double* __restrict__ dst, int tile0) {
   const int I = tiles[blockIdx.x] & 0xffff;
   int64_t ld;
-  const double* src = row_tile_ptr(p, I, lcol0, ld);
+  const double* src = row_tile_ptr(p, 0, I, lcol0, ld);
   double* d = dst + (int64_t)(I - tile0) * TILE * K;
   for (int idx = threadIdx.x; idx < (TILE / 2) * K; idx += blockDim.x) {
     const int r2 = idx % (TILE / 2), c = idx / (TILE / 2);
@@ -1168,7 +1179,7 @@ __global__ void __launch_bounds__(256) k_pack_tiles(GemmArgs p, const int* __res
   }
 }
 
-__global__ void k_reset_info(int* info) { *info = INT_MAX; }
+__global__ void k_reset_info(int* info) { info[blockIdx.x] = INT_MAX; }
 
 // ---- host: tile lists -------------------------------------------------------------------------
 // lower trapezoid J in [J0, J1), I in [J, nrows): valid tiles only, super-block by super-block
@@ -1285,8 +1296,9 @@ void vc_chol_invert_diag_tiles(const VcMatrix& M, VcCholWork& w, int64_t* launch
   for (int jt = 0; jt < M.nt; ++jt) {
     int64_t ld;
     double* diag = vc_host_tile_ptr(M, jt, jt, &ld);
-    if (potrf_use_b()) k_potrf128b<false><<<1, POTRF_THREADS, POTRFB_SMEM, w.st_main>>>(diag, ld, jt, w.linv, w.logdet_part, w.info);
-    else k_potrf128c<false><<<1, POTRF_THREADS, POTRFC_SMEM, w.st_main>>>(diag, ld, jt, w.linv, w.logdet_part, w.info);
+    const VcPotrfBatch one{1, 0, 0, 0};
+    if (potrf_use_b()) k_potrf128b<false><<<1, POTRF_THREADS, POTRFB_SMEM, w.st_main>>>(diag, ld, jt, w.linv, w.logdet_part, w.info, one);
+    else k_potrf128c<false><<<1, POTRF_THREADS, POTRFC_SMEM, w.st_main>>>(diag, ld, jt, w.linv, w.logdet_part, w.info, one);
     ++*launches;
   }
 }
@@ -1345,52 +1357,64 @@ void trace_dump(int nt, int nb) {
 }  // namespace
 
 void vc_launch_potrf(double* diag, int64_t lda, int jt, double* linv_all, double* logdet_part, int* info,
-                     bool legacy, cudaStream_t st, int64_t* launches) {
-  TraceScope ts("potrf", st, jt, 1);
-  if (legacy) k_potrf128<<<1, POTRF_THREADS, POTRF_SMEM, st>>>(diag, lda, jt, linv_all, logdet_part, info);
-  else if (potrf_use_b()) k_potrf128b<true><<<1, POTRF_THREADS, POTRFB_SMEM, st>>>(diag, lda, jt, linv_all, logdet_part, info);
-  else k_potrf128c<true><<<1, POTRF_THREADS, POTRFC_SMEM, st>>>(diag, lda, jt, linv_all, logdet_part, info);
+                     bool legacy, cudaStream_t st, int64_t* launches, VcPotrfBatch bat) {
+  TraceScope ts("potrf", st, jt, bat.n);
+  const int nb = std::max(bat.n, 1);
+  if (legacy) k_potrf128<<<nb, POTRF_THREADS, POTRF_SMEM, st>>>(diag, lda, jt, linv_all, logdet_part, info, bat);
+  else if (potrf_use_b()) k_potrf128b<true><<<nb, POTRF_THREADS, POTRFB_SMEM, st>>>(diag, lda, jt, linv_all, logdet_part, info, bat);
+  else k_potrf128c<true><<<nb, POTRF_THREADS, POTRFC_SMEM, st>>>(diag, lda, jt, linv_all, logdet_part, info, bat);
   ++*launches;
 }
 void vc_launch_trsm(const VcGemmArgs& g, int grid, cudaStream_t st, int64_t* launches) {
   if (grid <= 0) return;
   TraceScope ts("trsm", st, g.jt, grid);
-  k_trsm_panel<<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(g);
+  k_trsm_panel<<<dim3(grid, std::max(g.nbatch, 1)), GEMM_THREADS, GEMM_SMEM, st>>>(g);
   ++*launches;
 }
 void vc_launch_syrk(const VcGemmArgs& g, int num_sms, bool legacy, cudaStream_t st, int64_t* launches) {
   if (g.ntiles <= 0) return;
+  const int nbatch = std::max(g.nbatch, 1);
   if (legacy) {
     TraceScope ts(g.K == TILE ? "syrk128" : "syrk", st, g.ntiles, g.ntiles);
-    k_syrk_tiles<<<g.ntiles, GEMM_THREADS, GEMM_SMEM, st>>>(g);
+    k_syrk_tiles<<<dim3(g.ntiles, nbatch), GEMM_THREADS, GEMM_SMEM, st>>>(g);
     ++*launches;
     return;
   }
-  const int grid = std::min(g.ntiles, std::max(num_sms, 1));
+  const int total = g.ntiles * nbatch;       // linear index over (slot, tile)
+  const int grid = std::min(total, std::max(num_sms, 1));
   // A persistent grid walks ntiles / grid tiles per CTA; a remainder of a few tiles costs a whole extra
   // tile time on an almost empty machine.  Run a small remainder as 32-row strips instead (a quarter of
   // the time, same arithmetic).  VC_NO_STRIPS=1 disables.
   static const bool no_strips = getenv("VC_NO_STRIPS") != nullptr;
-  const int rem = g.ntiles % grid;
-  const int tail = (!no_strips && g.ntiles > grid && rem > 0 && 100 * rem <= 45 * grid) ? rem : 0;
+  const int rem = total % grid;
+  const int tail = (!no_strips && total > grid && rem > 0 && 100 * rem <= 45 * grid) ? rem : 0;
+  if (tail == 0) {
+    TraceScope ts(g.K == TILE ? "syrk128" : "syrk", st, total, grid);
+    k_syrk_ws<<<grid, WS_THREADS, WS_SMEM, st>>>(g);
+    ++*launches;
+    return;
+  }
+  // the persistent kernel takes the linear indices [0, total - tail), the strips the last `tail` ones
   VcGemmArgs m = g;
-  m.ntiles = g.ntiles - tail;
+  if (nbatch == 1) {
+    m.ntiles = total - tail;
+  } else {
+    // with several slots the cut does not fall on a slot boundary: k_syrk_ws stops at `limit`
+    m.lin_stop = total - tail;
+  }
   {
-    TraceScope ts(g.K == TILE ? "syrk128" : "syrk", st, m.ntiles, grid);
+    TraceScope ts(g.K == TILE ? "syrk128" : "syrk", st, total - tail, grid);
     k_syrk_ws<<<grid, WS_THREADS, WS_SMEM, st>>>(m);
     ++*launches;
   }
-  if (tail > 0) {
-    VcGemmArgs t = g;
-    t.tiles = g.tiles + m.ntiles;
-    t.ntiles = tail;
-    TraceScope ts("utail", st, tail, 4 * tail);
-    k_strip<<<4 * tail, GEMM_THREADS, GEMM_SMEM, st>>>(t);
-    ++*launches;
-  }
+  VcGemmArgs t = g;
+  t.lin_first = total - tail;                 // first linear index handled by the strips
+  TraceScope ts("utail", st, tail, 4 * tail);
+  k_strip<<<4 * tail, GEMM_THREADS, GEMM_SMEM, st>>>(t);
+  ++*launches;
 }
-void vc_launch_reset_info(int* info, cudaStream_t st, int64_t* launches) {
-  k_reset_info<<<1, 1, 0, st>>>(info);
+void vc_launch_reset_info(int* info, cudaStream_t st, int64_t* launches, int nbatch) {
+  k_reset_info<<<std::max(nbatch, 1), 1, 0, st>>>(info);
   ++*launches;
 }
 void vc_launch_pack_tiles(const VcGemmArgs& g, const int* tiles, int ntiles, int lcol0, int K, double* dst,
@@ -1404,6 +1428,8 @@ void vc_append_trapezoid(std::vector<int>& out, int J0, int J1, int nrows) { app
 static GemmArgs base_args(const VcMatrix& M) {
   GemmArgs g{};
   g.a = M.a; g.cb = M.cb; g.blk = M.blk; g.pr = 1; g.pc = 1; g.b = M.b; g.ldb = M.ldb; g.nt = M.nt;
+  g.nbatch = std::max(M.nbatch, 1); g.a_es = M.a_es; g.b_es = M.b_es;
+  g.linv_es = (int64_t)M.nt * TILE * TILE;
   return g;
 }
 
@@ -1421,15 +1447,17 @@ static void launch_update(const VcMatrix& M, const VcCholWork& w, const VcCholPl
 // (other stream) only overlaps if some SMs are left free.  Pick the number R of SMs to leave to the
 // panel so that max(panel time on R SMs, trailing update on num_sms - R SMs) is smallest.
 int vc_pick_reserved_sms(int num_sms, int rows_t /*row tiles below the panel*/, int nb,
-                         int rest_tiles, int* tiles_beside_panel) {
+                         int rest_tiles /*per slot*/, int* tiles_beside_panel, int nbatch) {
   *tiles_beside_panel = rest_tiles;
   if (rest_tiles <= 0) return 0;
   const double t_potrf = 45.0, t_tile128 = 20.0, t_tile_nb = 17.0 * nb;   // microseconds
   const double panel_serial = nb * (t_potrf + 2 * t_tile128);
-  const double panel_par = (nb + nb * (nb - 1) / 2.0) * rows_t * t_tile128;
+  const double panel_par = (nb + nb * (nb - 1) / 2.0) * rows_t * t_tile128 * nbatch;
+  rest_tiles *= nbatch;
   int best = 1;
   double best_t = 1e300, best_tp = 0.0;
-  for (int r = 1; r <= num_sms / 2; ++r) {
+  // every slot's diagonal tile is factored by its own CTA: the potrf chain needs nbatch SMs at once
+  for (int r = std::min(std::max(nbatch, 1), num_sms / 2); r <= num_sms / 2; ++r) {
     const double tp = panel_serial + panel_par / r;
     const double tu = (double)((rest_tiles + (num_sms - r) - 1) / (num_sms - r)) * t_tile_nb;
     const double t = std::max(tp, tu);
@@ -1439,7 +1467,7 @@ int vc_pick_reserved_sms(int num_sms, int rows_t /*row tiles below the panel*/, 
   // panel's estimated duration on num_sms - R CTAs, the remainder on the full machine afterwards.
   const double waves = 2.0 * best_tp / t_tile_nb;
   const double tiles = waves * (num_sms - best);
-  if (tiles < 0.7 * rest_tiles) {
+  if (nbatch == 1 && tiles < 0.7 * rest_tiles) {
     int nA = (int)(tiles / (num_sms - best) + 1.0) * (num_sms - best);
     *tiles_beside_panel = std::min(nA, rest_tiles);
   }
@@ -1455,10 +1483,8 @@ void vc_chol_factor(const VcMatrix& M, VcCholWork& w, int64_t* launches, int mod
   const bool ident = (mode == VC_SWEEP_SOLVE_IDENT);
   build_plan(pl, nt, nbt, nb, la, mode);
   cudaStream_t sm = w.st_main, sp = la ? w.st_panel : w.st_main;
-  if (!solve) {
-    k_reset_info<<<1, 1, 0, sm>>>(w.info);
-    ++*launches;
-  }
+  const int nbatch = std::max(M.nbatch, 1);
+  if (!solve) vc_launch_reset_info(w.info, sm, launches, nbatch);
   if (la) {
     VC_CUDA_TRY(cudaEventRecord(w.ev_update, sm));
     VC_CUDA_TRY(cudaStreamWaitEvent(sp, w.ev_update, 0));
@@ -1481,7 +1507,8 @@ void vc_chol_factor(const VcMatrix& M, VcCholWork& w, int64_t* launches, int mod
       if (!solve) {
         int64_t ld;
         double* diag = vc_host_tile_ptr(M, jt, jt, &ld);
-        vc_launch_potrf(diag, ld, jt, w.linv, w.logdet_part, w.info, w.legacy_potrf, sp, launches);
+        vc_launch_potrf(diag, ld, jt, w.linv, w.logdet_part, w.info, w.legacy_potrf, sp, launches,
+                        VcPotrfBatch{nbatch, M.a_es, (int64_t)nt * TILE * TILE, nt});
       }
       GemmArgs g = base_args(M);
       g.linv = w.linv + (int64_t)jt * TILE * TILE;
@@ -1517,7 +1544,7 @@ void vc_chol_factor(const VcMatrix& M, VcCholWork& w, int64_t* launches, int mod
     VC_CUDA_TRY(cudaStreamWaitEvent(sp, w.ev_col, 0));
     const int rest_tiles = pl.calls[c_rest].ntiles;
     int nA = rest_tiles;
-    int reserve = w.legacy_syrk ? 0 : vc_pick_reserved_sms(w.num_sms, nt + nbt - oe, nb, rest_tiles, &nA);
+    int reserve = w.legacy_syrk ? 0 : vc_pick_reserved_sms(w.num_sms, nt + nbt - oe, nb, rest_tiles, &nA, nbatch);
     {  // tuning overrides: VC_RESERVE_SMS = fixed R, VC_NO_SPLIT = run the whole rest update on num_sms - R
       static const int fixed = getenv("VC_RESERVE_SMS") ? atoi(getenv("VC_RESERVE_SMS")) : -1;
       static const bool nosplit = getenv("VC_NO_SPLIT") != nullptr;

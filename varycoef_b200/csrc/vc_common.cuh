@@ -90,7 +90,9 @@ struct VcMatrix {        // padded Sigma / factor in HBM (lower block-column tra
   const VcColBlock* cb;       // device table, one entry per local block column
   const VcColBlock* cb_host;  // the same table on the host (owned by the handle)
   int blk;               // tile columns per block column
-  int64_t a_doubles;     // size of the allocation behind `a`
+  int64_t a_doubles;     // doubles of ONE evaluation slot behind `a`
+  int nbatch;            // evaluation slots swept by one launch (batched small-n path); slot e lives at
+  int64_t a_es, b_es;    //   a + e * a_es, b + e * b_es
   int64_t n;             // real order
   int64_t n_pad;         // multiple of VC_TILE
   int nt;                // n_pad / VC_TILE  (column tiles)
@@ -100,8 +102,9 @@ struct VcMatrix {        // padded Sigma / factor in HBM (lower block-column tra
 };
 
 // vc_build.cu
+// th_dev != nullptr: batched build, slot e (grid.y) uses th_dev[e]; th then only supplies the model (cov, taper, q)
 void vc_launch_build(const VcMatrix& M, const VcTheta& th, int d, const double* locs_pad,
-                     const double* w_pad, cudaStream_t st, int64_t* launches);
+                     const double* w_pad, cudaStream_t st, int64_t* launches, const VcTheta* th_dev = nullptr);
 void vc_launch_border(const VcMatrix& M, int p, const double* x_pad, const double* y_pad,
                       cudaStream_t st, int64_t* launches);
 void vc_launch_sigma_full(double* out, int64_t n, int64_t n_pad, const VcTheta& th, int d,
@@ -126,6 +129,8 @@ struct VcOpSrc {          // where a GEMM operand row tile comes from
 struct VcGemmArgs {       // by-value argument block of k_trsm_panel / k_syrk_ws / k_syrk_tiles
   double* a;              // (local) matrix, row tiles 0 .. nt-1 (global numbering)
   const VcColBlock* cb;   // its block-column table
+  int nbatch;             // evaluation slots handled by this launch (grid.y, or the persistent tile index / ntiles)
+  int64_t a_es, b_es, linv_es;   // doubles between consecutive slots of a / b / linv
   double* b;              // border rows, row tiles nt .. nt+nbt-1
   int64_t ldb;
   int nt;
@@ -139,6 +144,7 @@ struct VcGemmArgs {       // by-value argument block of k_trsm_panel / k_syrk_ws
   int ntiles;
   VcOpSrc src_a, src_b;   // operand sources of the update kernels
   int i_skip;             // TRSM without tile list: main row tiles start at jt + 1 + i_skip
+  int lin_first, lin_stop;  // update kernels: first linear (slot, tile) index of k_strip / stop index of k_syrk_ws (0 = all)
 };
 struct VcUpdateCall {     // one trailing / inner update of the factorisation plan
   int k0, K;             // panel columns [k0, k0 + K)
@@ -153,9 +159,9 @@ struct VcCholPlan {       // tile lists of every update launch, precomputed per 
   int64_t tiles_cap = 0;
 };
 struct VcCholWork {
-  double* linv;          // nt x (128 x 128): inverse of every diagonal factor tile
-  double* logdet_part;   // nt partial sums of log L_jj
-  int* info;             // first failing leading minor (INT_MAX if none)
+  double* linv;          // per slot: nt x (128 x 128), the inverse of every diagonal factor tile
+  double* logdet_part;   // per slot: nt partial sums of log L_jj
+  int* info;             // per slot: first failing leading minor (INT_MAX if none)
   int nb_tiles;          // outer block in tiles (nb_outer / 128)
   bool lookahead;
   bool legacy_syrk;      // use the non-persistent cp.async SYRK kernel (A/B testing)
@@ -179,15 +185,16 @@ inline double* vc_host_tile_ptr(const VcMatrix& M, int lI, int lJ, int64_t* ld) 
   *ld = e.ld;
   return M.a + e.off + (int64_t)(lI - e.r0) * VC_TILE + (int64_t)(lJ % M.blk) * VC_TILE * (int64_t)e.ld;
 }
+struct VcPotrfBatch { int n; int64_t a_es, linv_es; int nt; };   // slot e: diag + e a_es, linv + e linv_es, logdet + e nt, info + e
 void vc_launch_potrf(double* diag, int64_t lda, int jt, double* linv_all, double* logdet_part, int* info,
-                     bool legacy, cudaStream_t st, int64_t* launches);
+                     bool legacy, cudaStream_t st, int64_t* launches, VcPotrfBatch bat = VcPotrfBatch{1, 0, 0, 0});
 void vc_launch_trsm(const VcGemmArgs& g, int grid, cudaStream_t st, int64_t* launches);
 void vc_launch_syrk(const VcGemmArgs& g, int num_sms, bool legacy, cudaStream_t st, int64_t* launches);
-void vc_launch_reset_info(int* info, cudaStream_t st, int64_t* launches);
+void vc_launch_reset_info(int* info, cudaStream_t st, int64_t* launches, int nbatch = 1);
 void vc_launch_pack_tiles(const VcGemmArgs& g, const int* tiles, int ntiles, int lcol0, int K, double* dst,
                           int tile0, cudaStream_t st, int64_t* launches);
 void vc_append_trapezoid(std::vector<int>& out, int J0, int J1, int nrows);
-int vc_pick_reserved_sms(int num_sms, int rows_t, int nb, int rest_tiles, int* tiles_beside_panel);
+int vc_pick_reserved_sms(int num_sms, int rows_t, int nb, int rest_tiles, int* tiles_beside_panel, int nbatch = 1);
 
 // vc_finalize.cu
 struct VcFinalWork {
@@ -195,10 +202,13 @@ struct VcFinalWork {
   double* quad_part;     // blocks x 2
   int blocks;
 };
+// njobs finalize jobs in one launch: job j reads the whitened border / log-det / info of slot job_slot_dev[j]
+// (nullptr: slot 0) and mu_in_dev + 128 j, writes result_dev + VC_RES_STRIDE j; fw holds njobs partial buffers;
+// gram_out_dev receives the Gram matrix of slot 0
 void vc_launch_finalize(const VcMatrix& M, int p, int mu_mode, const double* mu_in_dev,
                         const double* logdet_part, const int* info, VcFinalWork& fw,
                         double* result_dev, cudaStream_t st, int64_t* launches,
-                        double* gram_out_dev = nullptr);
+                        double* gram_out_dev = nullptr, int njobs = 1, const int* job_slot_dev = nullptr);
 void vc_launch_gram_local(const double* b, int64_t ldb, int64_t ncols, int p, VcFinalWork& fw, double* gram_dd,
                           cudaStream_t st, int64_t* launches);
 void vc_launch_sum(const double* v, int n, double* out, cudaStream_t st, int64_t* launches);

@@ -10,6 +10,7 @@
 #include "vc_common.cuh"
 #include <limits.h>
 #include <math.h>
+#include <algorithm>
 
 namespace {
 
@@ -37,10 +38,12 @@ __device__ __forceinline__ void dd_add(double& hi, double& lo, double ah, double
 // partial Gram of the (p+1) border rows over a slice of columns; pairs (a <= b) are linearised
 __global__ void __launch_bounds__(FIN_THREADS)
 k_gram_partial(const double* __restrict__ b, int64_t ldb, int64_t n, int p,
-               double* __restrict__ part) {
+               double* __restrict__ part, int64_t b_es, const int* __restrict__ job_slot) {
   extern __shared__ double sm[];
   const int m = p + 1;
   const int npairs = m * (m + 1) / 2;
+  b += (job_slot ? job_slot[blockIdx.y] : 0) * b_es;        // job blockIdx.y reads the border of its slot
+  part += (int64_t)blockIdx.y * gridDim.x * 2 * npairs;
   double* z = sm;                         // m x CHUNK
   double* acc = z + m * CHUNK;            // npairs x 2
   const int tid = threadIdx.x;
@@ -78,10 +81,21 @@ k_gram_partial(const double* __restrict__ b, int64_t ldb, int64_t n, int p,
 __global__ void __launch_bounds__(FIN_THREADS)
 k_solve_mu(const double* __restrict__ part, int blocks, int p, int mu_mode,
            const double* __restrict__ mu_in, const double* __restrict__ logdet_part, int nt,
-           const int* __restrict__ info, double* __restrict__ res, double* __restrict__ gram_out) {
+           const int* __restrict__ info, double* __restrict__ res, double* __restrict__ gram_out,
+           const int* __restrict__ job_slot) {
   extern __shared__ double sm[];
   const int m = p + 1;
   const int npairs = m * (m + 1) / 2;
+  {                                                          // job blockIdx.x of a batched launch
+    const int j = blockIdx.x, slot = job_slot ? job_slot[j] : 0;
+    part += (int64_t)j * blocks * 2 * npairs;
+    if (mu_in) mu_in += (int64_t)j * 128;
+    logdet_part += (int64_t)slot * nt;
+    info += slot;
+    res += (int64_t)j * VC_RES_STRIDE;
+    // the Gram matrix kept for vc_post is the one of slot 0 = the last evaluation (first job that reads slot 0)
+    if (slot != 0) gram_out = nullptr;
+  }
   double* G = sm;                 // m x m (column-major, symmetric)
   double* mu = G + m * m;         // p
   const int tid = threadIdx.x;
@@ -151,10 +165,14 @@ k_solve_mu(const double* __restrict__ part, int blocks, int p, int mu_mode,
 // partial sums of (Z_y - Z_X mu)^2 over a slice of columns
 __global__ void __launch_bounds__(FIN_THREADS)
 k_quad_partial(const double* __restrict__ b, int64_t ldb, int64_t n, int p,
-               const double* __restrict__ res, double* __restrict__ part) {
+               const double* __restrict__ res, double* __restrict__ part, int64_t b_es,
+               const int* __restrict__ job_slot) {
   __shared__ double smu[128];
   __shared__ double shi[FIN_THREADS], slo[FIN_THREADS];
   const int tid = threadIdx.x;
+  b += (job_slot ? job_slot[blockIdx.y] : 0) * b_es;        // job blockIdx.y reads the border of its slot
+  res += (int64_t)blockIdx.y * VC_RES_STRIDE;
+  part += (int64_t)blockIdx.y * gridDim.x * 2;
   if (tid < p) smu[tid] = res[VC_RES_MU + tid];
   __syncthreads();
   const int64_t per = (n + gridDim.x - 1) / gridDim.x;
@@ -184,6 +202,8 @@ k_quad_partial(const double* __restrict__ b, int64_t ldb, int64_t n, int p,
 }
 
 __global__ void k_assemble(const double* __restrict__ part, int blocks, int64_t n, double* __restrict__ res) {
+  part += (int64_t)blockIdx.x * blocks * 2;                 // job of a batched launch
+  res += (int64_t)blockIdx.x * VC_RES_STRIDE;
   double hi = 0.0, lo = 0.0;
   for (int b = 0; b < blocks; ++b) dd_add(hi, lo, part[2 * b], part[2 * b + 1]);
   const double quad = hi + lo;
@@ -245,7 +265,7 @@ void vc_launch_gram_local(const double* b, int64_t ldb, int64_t ncols, int p, Vc
   const int m = p + 1, npairs = m * (m + 1) / 2;
   const size_t sm1 = ((size_t)m * CHUNK + 2 * (size_t)npairs) * sizeof(double);
   cudaFuncSetAttribute(k_gram_partial, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  k_gram_partial<<<fw.blocks, FIN_THREADS, sm1, st>>>(b, ldb, ncols, p, fw.gram_part);
+  k_gram_partial<<<fw.blocks, FIN_THREADS, sm1, st>>>(b, ldb, ncols, p, fw.gram_part, 0, nullptr);
   k_reduce_dd<<<(npairs + 127) / 128, 128, 0, st>>>(fw.gram_part, fw.blocks, npairs, gram_dd);
   *launches += 2;
 }
@@ -259,12 +279,12 @@ void vc_launch_solve_reduced(const double* gram_dd, int p, int mu_mode, const do
   const int m = p + 1;
   const size_t sm2 = ((size_t)m * m + p + 1) * sizeof(double);
   cudaFuncSetAttribute(k_solve_mu, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  k_solve_mu<<<1, FIN_THREADS, sm2, st>>>(gram_dd, 1, p, mu_mode, mu_in_dev, logdet_sum, 1, info, result_dev, gram_out);
+  k_solve_mu<<<1, FIN_THREADS, sm2, st>>>(gram_dd, 1, p, mu_mode, mu_in_dev, logdet_sum, 1, info, result_dev, gram_out, nullptr);
   ++*launches;
 }
 void vc_launch_quad_local(const double* b, int64_t ldb, int64_t ncols, int p, const double* result_dev,
                           VcFinalWork& fw, double* quad_dd, cudaStream_t st, int64_t* launches) {
-  k_quad_partial<<<fw.blocks, FIN_THREADS, 0, st>>>(b, ldb, ncols, p, result_dev, fw.quad_part);
+  k_quad_partial<<<fw.blocks, FIN_THREADS, 0, st>>>(b, ldb, ncols, p, result_dev, fw.quad_part, 0, nullptr);
   k_reduce_dd<<<1, 32, 0, st>>>(fw.quad_part, fw.blocks, 1, quad_dd);
   *launches += 2;
 }
@@ -276,7 +296,8 @@ void vc_launch_assemble_reduced(const double* quad_dd, int64_t n, double* result
 
 void vc_launch_finalize(const VcMatrix& M, int p, int mu_mode, const double* mu_in_dev,
                         const double* logdet_part, const int* info, VcFinalWork& fw,
-                        double* result_dev, cudaStream_t st, int64_t* launches, double* gram_out_dev) {
+                        double* result_dev, cudaStream_t st, int64_t* launches, double* gram_out_dev,
+                        int njobs, const int* job_slot_dev) {
   const int m = p + 1;
   const int npairs = m * (m + 1) / 2;
   const size_t sm1 = ((size_t)m * CHUNK + 2 * (size_t)npairs) * sizeof(double);
@@ -290,11 +311,12 @@ void vc_launch_finalize(const VcMatrix& M, int p, int mu_mode, const double* mu_
     VC_CUDA_TRY(cudaFuncSetAttribute(k_solve_mu, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr = true;
   }
-  k_gram_partial<<<fw.blocks, FIN_THREADS, sm1, st>>>(M.b, M.ldb, M.n, p, fw.gram_part);
-  k_solve_mu<<<1, FIN_THREADS, sm2, st>>>(fw.gram_part, fw.blocks, p, mu_mode, mu_in_dev, logdet_part,
-                                          M.nt, info, result_dev, gram_out_dev);
-  k_quad_partial<<<fw.blocks, FIN_THREADS, 0, st>>>(M.b, M.ldb, M.n, p, result_dev, fw.quad_part);
-  k_assemble<<<1, 1, 0, st>>>(fw.quad_part, fw.blocks, M.n, result_dev);
+  const unsigned nj = (unsigned)std::max(njobs, 1);
+  k_gram_partial<<<dim3(fw.blocks, nj), FIN_THREADS, sm1, st>>>(M.b, M.ldb, M.n, p, fw.gram_part, M.b_es, job_slot_dev);
+  k_solve_mu<<<nj, FIN_THREADS, sm2, st>>>(fw.gram_part, fw.blocks, p, mu_mode, mu_in_dev, logdet_part,
+                                           M.nt, info, result_dev, gram_out_dev, job_slot_dev);
+  k_quad_partial<<<dim3(fw.blocks, nj), FIN_THREADS, 0, st>>>(M.b, M.ldb, M.n, p, result_dev, fw.quad_part, M.b_es, job_slot_dev);
+  k_assemble<<<nj, 1, 0, st>>>(fw.quad_part, fw.blocks, M.n, result_dev);
   *launches += 4;
 }
 

@@ -2,19 +2,6 @@
 #pragma once
 #include "vc_common.cuh"
 
-// An extra evaluation lane: its own matrix, factor workspace and streams.  vc_n2ll_batch spreads the
-// evaluations of a batch over the lanes when one evaluation cannot fill the GPU (n_pad <= 16384), the
-// single-GPU analogue of the reference's optimParallel fan-out (R-pkg/R/SVC_mle.R:164-200).
-struct VcLane {
-  VcMatrix M{};
-  VcCholWork cw{};
-  VcFinalWork fw{};
-  double* gram_dev = nullptr;
-  cudaStream_t st_main = nullptr, st_panel = nullptr;
-  cudaEvent_t ev_done = nullptr;
-  std::vector<double> factor_theta;
-};
-
 struct vc_handle {
   vc_config cfg;
   int64_t n = 0, n_pad = 0;
@@ -35,11 +22,20 @@ struct vc_handle {
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // t0, after build, after chol, after finalize
   vc_timing last_timing{};
   int last_info = 0;
+  int last_rec = 0;                  // result record of the last valid evaluation of the last batch
   bool factor_valid = false;
   std::vector<double> factor_theta;  // theta of the factor resident in M (empty = none)
   double* gram_dev = nullptr;        // (p+1)^2 Gram of the whitened [X y] of the last evaluation
-  std::vector<VcLane*> lanes;        // extra lanes (lane 0 is the handle itself), created on demand
-  cudaEvent_t ev_inputs = nullptr;   // batch inputs (mu) staged on st_main
+  // Evaluation slots: M.a, M.b, cw.linv, cw.logdet_part, cw.info hold `slots` evaluations back to back.  A batch
+  // (vc_n2ll_batch: optim's gradient / Hessian stencil, the analogue of the reference's optimParallel fan-out,
+  // R-pkg/R/SVC_mle.R:164-200) is swept by ONE sequence of launches with the slot index in the grid, so that
+  // small and mid-size problems fill the 148 SMs; slot 0 always receives the last evaluation of a batch.
+  int slots = 1;
+  VcTheta* thetas_dev = nullptr;     // slots entries: parameters of the evaluations of the group in flight
+  VcTheta* thetas_host = nullptr;    // pinned staging
+  int* job_slot_dev = nullptr;       // result_slots entries: slot each finalize job reads
+  int* job_slot_host = nullptr;      // pinned staging
+  double* mu_host = nullptr;         // pinned staging of caller-supplied mu (128 x result_slots)
   int64_t launches = 0;
   std::string err;
   // distributed state lives in vc_dist.cu
