@@ -151,6 +151,15 @@ VC_API int vc_predict(vc_handle* h, const double* theta, const double* mu, int64
                const double* newlocs, const double* newX, const double* newW,
                double* eff, double* y_pred, double* y_var);
 
+/*
+ * med_dist of MLE_computation (R-pkg/R/SVC_mle.R:39-45, dense branch): median(as.numeric(d)) over the full
+ * n x n distance matrix (zero diagonal and both triangles included), from which the default init / bounds of
+ * the optimiser are derived (R-pkg/R/utils.R:336-396).  Exact (radix select on recomputed tile-local
+ * distances), nothing n x n is held.  Stand-alone: no handle.  locs: n x d column-major.
+ */
+VC_API int vc_median_dist(int32_t device, int64_t n, int32_t d, const double* locs, int32_t dist_method,
+                          double minkowski_p, double* med_out, int32_t* launches_out);
+
 /* diagnostics */
 VC_API int vc_timings(vc_handle* h, vc_timing* out);
 VC_API int vc_last_info(vc_handle* h);              /* order of the failing leading minor, 0 if none */

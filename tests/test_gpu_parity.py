@@ -662,6 +662,26 @@ def test_config_c3_n50000_headline_against_cusolver_third_path():
         assert _rel(r3["mu"], 3.0 * r["mu"]) <= 1e-10
 
 
+def test_median_dist_on_gpu_is_exactly_the_host_median():
+    """med_dist (R-pkg/R/SVC_mle.R:39-45): the radix select over recomputed distances (csrc/vc_median.cu) must
+    return EXACTLY median(as.numeric(d)) of the full n x n matrix -- odd and even n, duplicates, zero diagonal,
+    every dist method whose arithmetic is correctly rounded."""
+    from varycoef_b200.svc_mle import median_dist
+    o = _oracle()
+    rng = np.random.default_rng(3)
+    for n, d in ((1, 1), (2, 2), (3, 1), (7, 1), (50, 2), (128, 2), (129, 3), (501, 2), (2000, 2)):
+        locs = rng.uniform(0, 5, (n, d))
+        assert median_dist(locs) == float(np.median(o.own_dist(locs))), (n, d)
+    locs = rng.integers(0, 4, (300, 2)).astype(float)          # many ties and collocated points
+    assert median_dist(locs) == float(np.median(o.own_dist(locs)))
+    locs = rng.uniform(0, 5, (400, 3))
+    for m in ("maximum", "manhattan"):
+        assert median_dist(locs, m) == float(np.median(o.own_dist(locs, method=m))), m
+    assert abs(median_dist(locs, "minkowski", 3.0) - float(np.median(o.own_dist(locs, method="minkowski", p=3.0)))) < 1e-13
+    locs = rng.uniform(0, 70, (5000, 2))                        # beyond what the host holds comfortably: blocked oracle
+    assert median_dist(locs) == o.median_dist(locs)
+
+
 def test_fallback_kernels_agree_with_default_path():
     """VC_FLAG_LEGACY_POTRF (unblocked diagonal-tile kernel) and VC_FLAG_NO_LOOKAHEAD give the same
     likelihood as the default kernels up to rounding."""

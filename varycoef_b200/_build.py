@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libvarycoef_b200.so")
-SOURCES = ["vc_api.cu", "vc_build.cu", "vc_chol.cu", "vc_finalize.cu", "vc_extra.cu", "vc_dist.cu"]
+SOURCES = ["vc_api.cu", "vc_build.cu", "vc_chol.cu", "vc_finalize.cu", "vc_extra.cu", "vc_dist.cu", "vc_median.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-Xptxas", "-v",

@@ -63,6 +63,7 @@ SIGNATURES = {
     "vc_get_chol": (C.c_int, [C.c_void_p, _dp]),
     "vc_get_whitened": (C.c_int, [C.c_void_p, _dp]),
     "vc_gls_chol": (C.c_int, [C.c_int32, C.c_int64, C.c_int32, _dp, _dp, _dp, _dp]),
+    "vc_median_dist": (C.c_int, [C.c_int32, C.c_int64, C.c_int32, _dp, C.c_int32, C.c_double, _dp, C.POINTER(C.c_int32)]),
     "vc_post": (C.c_int, [C.c_void_p, _dp, _dp, _dp, C.POINTER(C.c_double)]),
     "vc_predict": (C.c_int, [C.c_void_p, _dp, _dp, C.c_int64, _dp, _dp, _dp, _dp, _dp, _dp]),
     "vc_timings": (C.c_int, [C.c_void_p, C.POINTER(VcTiming)]),

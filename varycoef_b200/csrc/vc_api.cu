@@ -280,12 +280,14 @@ static int slot_cap(const vc_handle* h) {
   if (h->dist) return 1;
   static const int env_cap = getenv("VC_MAX_SLOTS") ? atoi(getenv("VC_MAX_SLOTS")) : 0;   // tuning / debugging
   if (h->n_pad > 24576) return 1;
+  if (h->slot_cap_cached > 0) return h->slot_cap_cached;
   const double bytes = 8.0 * ((double)h->M.a_doubles + (double)h->M.ldb * h->n_pad + (double)h->M.nt * VC_TILE * VC_TILE);
   size_t free_b = 0, total_b = 0;
   cudaMemGetInfo(&free_b, &total_b);
   const double budget = std::min(24e9, 0.5 * ((double)free_b + (double)h->slots * bytes));
   int cap = (int)std::max(1.0, std::min(32.0, floor(budget / bytes)));
   if (env_cap >= 1) cap = std::min(cap, env_cap);
+  const_cast<vc_handle*>(h)->slot_cap_cached = cap;
   return cap;
 }
 

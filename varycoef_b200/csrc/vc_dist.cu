@@ -355,6 +355,7 @@ int vc_dist_n2ll(vc_handle* h, const double* theta, int32_t mu_mode, const doubl
     VcGemmArgs base{};
     base.a = h->M.a; base.cb = h->M.cb; base.b = h->M.b; base.ldb = h->M.ldb; base.nt = nt;
     base.blk = nb; base.pr = D->pr; base.pc = D->pc;
+    base.nbatch = 1;
     // Lookahead: the panel phase of block s+1 (factor / broadcasts / solves, stream sp) overlaps the
     // "rest" part of the trailing update of block s (stream sm).  All NCCL calls are on sp, in the
     // same order on every rank.  A persistent update kernel never yields an SM, so the rest update

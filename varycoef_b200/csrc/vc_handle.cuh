@@ -31,6 +31,7 @@ struct vc_handle {
   // R-pkg/R/SVC_mle.R:164-200) is swept by ONE sequence of launches with the slot index in the grid, so that
   // small and mid-size problems fill the 148 SMs; slot 0 always receives the last evaluation of a batch.
   int slots = 1;
+  int slot_cap_cached = 0;           // slot_cap(): queried once (cudaMemGetInfo is slow)
   VcTheta* thetas_dev = nullptr;     // slots entries: parameters of the evaluations of the group in flight
   VcTheta* thetas_host = nullptr;    // pinned staging
   int* job_slot_dev = nullptr;       // result_slots entries: slot each finalize job reads

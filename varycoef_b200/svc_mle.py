@@ -81,79 +81,17 @@ def init_bounds_optim(control, p, q, id_obj, med_dist, y_var, OLS_mu):
     return {"lower": lower, "init": init, "upper": upper}
 
 
-def _pair_block(a, b, method, p):
-    acc = np.zeros((a.shape[0], b.shape[0]))
-    for c in range(a.shape[1]):
-        dev = np.abs(a[:, c][:, None] - b[:, c][None, :])
-        if method == "euclidean":
-            acc += dev * dev
-        elif method == "maximum":
-            np.maximum(acc, dev, out=acc)
-        elif method == "manhattan":
-            acc += dev
-        else:
-            acc += dev ** p
-    if method == "euclidean":
-        return np.sqrt(acc)
-    if method == "minkowski":
-        return acc ** (1.0 / p)
-    return acc
-
-
-def median_dist(locs, method="euclidean", p=2.0, block=2048):
-    """median(as.numeric(d)) over the FULL n x n distance matrix, zero diagonal and both
-    triangles included (SVC_mle.R:41-43), without holding the matrix: exact selection by a
-    histogram pass plus a refinement pass over the strictly-lower pairs."""
-    locs = np.asarray(locs, dtype=np.float64)
-    if locs.ndim == 1:
-        locs = locs[:, None]
-    n = locs.shape[0]
-    N = n * n
-    # order statistics needed (0-based) in the full multiset = n zeros + each lower pair twice
-    ranks = [N // 2] if N % 2 == 1 else [N // 2 - 1, N // 2]
-
-    def lower_blocks():
-        for i0 in range(0, n, block):
-            a = locs[i0:i0 + block]
-            for j0 in range(0, i0 + 1, block):
-                d = _pair_block(a, locs[j0:j0 + block], method, p)
-                if j0 == i0:
-                    yield d[np.tril_indices(d.shape[0], -1, d.shape[1])]
-                else:
-                    yield d.ravel()
-
-    if n * (n - 1) // 2 <= 4_000_000:
-        low = np.concatenate([b for b in lower_blocks()]) if n > 1 else np.zeros(0)
-        low.sort()
-        vals = []
-        for r in ranks:
-            vals.append(0.0 if r < n else float(low[(r - n) // 2]))
-        return float(np.mean(vals))
-    dmax = 0.0
-    for b in lower_blocks():
-        if b.size:
-            dmax = max(dmax, float(b.max()))
-    nb = 1 << 16
-    hist = np.zeros(nb, dtype=np.int64)
-    scale = nb / (dmax * (1 + 1e-12) + 1e-300)
-    for b in lower_blocks():
-        hist += np.bincount(np.minimum((b * scale).astype(np.int64), nb - 1), minlength=nb)
-    cum = np.cumsum(hist)
-    vals = []
-    for r in ranks:
-        if r < n:
-            vals.append(0.0)
-            continue
-        k = (r - n) // 2                      # rank among the lower pairs
-        bi = int(np.searchsorted(cum, k, side="right"))
-        before = int(cum[bi - 1]) if bi > 0 else 0
-        sel = []
-        for b in lower_blocks():
-            idx = np.minimum((b * scale).astype(np.int64), nb - 1)
-            sel.append(b[idx == bi])
-        sel = np.sort(np.concatenate(sel))
-        vals.append(float(sel[k - before]))
-    return float(np.mean(vals))
+def median_dist(locs, method="euclidean", p=2.0, device=0):
+    """median(as.numeric(d)) over the FULL n x n distance matrix, zero diagonal and both triangles included
+    (SVC_mle.R:39-45), on the GPU: exact radix select over recomputed tile-local distances
+    (csrc/vc_median.cu), nothing n x n is ever held.  Bit-identical to the host median of stats::dist."""
+    import ctypes as C
+    from . import _lib
+    locs = _lib.as_f64(locs, 2)
+    out = C.c_double()
+    _lib.check(_lib.lib().vc_median_dist(int(device), locs.shape[0], locs.shape[1], _lib.ptr(locs),
+                                         _lib.DIST_IDS[method], float(p), C.byref(out), None), None)
+    return out.value
 
 
 def _ols(X, y):
