@@ -89,6 +89,19 @@ VC_API int vc_config_default(vc_config* cfg);
 VC_API int vc_create(vc_handle** h, const vc_config* cfg, int64_t n, int32_t d, int32_t p, int32_t q,
               const double* locs, const double* X, const double* W, const double* y);
 
+/*
+ * The same objective on SEVERAL GPUs of one process: one replica of the O(n) inputs per device;
+ * vc_n2ll_batch spreads the distinct thetas of a batch over the devices (no collective; results are gathered on
+ * the host).  This is the GPU analogue of the reference's optimParallel fan-out over PSOCK workers
+ * (R-pkg/R/SVC_mle.R:164-200, control$parallel): optim's finite-difference and Hessian stencils are evaluated by
+ * all devices at once.  Every other entry point acts on the device that ran the last evaluation.
+ * cfg->device is ignored; devices[] may name a device more than once.
+ */
+VC_API int vc_create_multi(vc_handle** h, const vc_config* cfg, int64_t n, int32_t d, int32_t p, int32_t q,
+                    const double* locs, const double* X, const double* W, const double* y,
+                    const int32_t* devices, int32_t ndev);
+VC_API int32_t vc_device_count(vc_handle* h);       /* devices behind the handle (1 unless vc_create_multi) */
+
 /* re-upload the O(n) inputs of an existing handle (same shapes); any pointer may be NULL = keep */
 VC_API int vc_set_data(vc_handle* h, const double* locs, const double* X, const double* W, const double* y);
 

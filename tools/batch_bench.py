@@ -33,6 +33,7 @@ def main():
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--cov", default="exp")
     ap.add_argument("--out", default="")
+    ap.add_argument("--nb", type=int, default=0, help="outer Cholesky block (0 = auto)")
     a = ap.parse_args()
     peak = C.c_double(0.0)
     _lib.lib().vc_probe_dmma_peak(0, 20000, C.byref(peak))
@@ -42,7 +43,7 @@ def main():
         locs, X, y = synth(n, p, 5 + n)
         base = np.array([1.3, 0.7, 2.1, 0.4, 0.9, 1.1, 0.35])
         xs = np.vstack([base * (1 + 0.003 * k) for k in range(a.m)])
-        with SVCObjective(y, X, locs, cov_name=a.cov, profileLik=True) as obj:
+        with SVCObjective(y, X, locs, cov_name=a.cov, profileLik=True, nb_outer=a.nb) as obj:
             single = np.array([obj.n2LL(x) for x in xs])
             batch = obj.n2LL_batch(xs)
             t_single, t_batch = 1e30, 1e30
@@ -55,7 +56,7 @@ def main():
                 obj.n2LL_batch(xs)
                 t_batch = min(t_batch, (time.perf_counter() - t0) / a.m)
             fl = n ** 3 / 3.0
-            rows.append({"n": n, "m": a.m, "single_ms": t_single * 1e3, "batch_ms_per_eval": t_batch * 1e3,
+            rows.append({"n": n, "m": a.m, "nb": a.nb, "single_ms": t_single * 1e3, "batch_ms_per_eval": t_batch * 1e3,
                          "single_tflops": fl / t_single / 1e12, "batch_tflops": fl / t_batch / 1e12,
                          "batch_frac_of_peak": fl / t_batch / 1e12 / peak.value, "speedup": t_single / t_batch,
                          "bit_identical": bool(np.array_equal(single, batch))})

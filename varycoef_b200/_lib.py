@@ -54,6 +54,9 @@ SIGNATURES = {
     "vc_config_default": (C.c_int, [C.POINTER(VcConfig)]),
     "vc_create": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(VcConfig), C.c_int64, C.c_int32, C.c_int32,
                             C.c_int32, _dp, _dp, _dp, _dp]),
+    "vc_create_multi": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(VcConfig), C.c_int64, C.c_int32, C.c_int32,
+                                  C.c_int32, _dp, _dp, _dp, _dp, C.POINTER(C.c_int32), C.c_int32]),
+    "vc_device_count": (C.c_int32, [C.c_void_p]),
     "vc_set_data": (C.c_int, [C.c_void_p, _dp, _dp, _dp, _dp]),
     "vc_destroy": (None, [C.c_void_p]),
     "vc_n2ll": (C.c_int, [C.c_void_p, _dp, C.c_int32, _dp, _dp, _dp, _dp, _dp]),

@@ -6,6 +6,7 @@
 #include <limits.h>
 #include <new>
 #include <algorithm>
+#include <thread>
 
 static thread_local std::string g_create_error;
 
@@ -57,6 +58,11 @@ int vc_validate_cfg(const vc_config* cfg, int64_t n, int d, int p, int q, std::s
 
 void vc_free_handle(vc_handle* h) {
   if (!h) return;
+  if (!h->kids.empty()) {
+    for (vc_handle* k : h->kids) vc_free_handle(k);
+    delete h;
+    return;
+  }
   cudaSetDevice(h->device);
   if (h->dist) vc_dist_destroy(h);
   cudaFree(h->cb_dev);
@@ -181,9 +187,9 @@ vc_handle* vc_alloc_common(const vc_config* cfg, int64_t n, int d, int p, int q,
       VC_CUDA_TRY(cudaGetDeviceProperties(&prop, h->device));
       h->cw.num_sms = prop.multiProcessorCount;
     }
-    // outer block: measured best 256 for n <= 12k, 512 up to 40k, 1024 beyond (profiles/r01_block_sweep.md)
-    // measured (profiles/r01_block_sweep.md, r01_panel_chain.md): 128 up to n = 4096, 256 up to 12288, 512, 1024 from 40000
-    const int nb_auto = np >= 40000 ? 1024 : (np <= 4096 ? 128 : (np <= 12288 ? 256 : 512));
+    // outer block = storage block.  Measured with batches of 16 (the stencils optim evaluates) and single
+    // evaluations (profiles/r02_batch_small_n.md): 256 up to n = 4096, 512 up to 40 000, 1024 beyond
+    const int nb_auto = np >= 40000 ? 1024 : (np <= 4096 ? 256 : 512);
     h->cw.nb_tiles = (cfg->nb_outer > 0 ? cfg->nb_outer : nb_auto) / VC_TILE;
     h->cw.lookahead = !(cfg->flags & VC_FLAG_NO_LOOKAHEAD);
     h->cw.st_main = h->st_main; h->cw.st_panel = h->st_panel;
@@ -238,9 +244,102 @@ extern "C" int vc_create(vc_handle** out, const vc_config* cfg_in, int64_t n, in
 
 extern "C" void vc_destroy(vc_handle* h) { vc_free_handle(h); }
 
+// One process, several GPUs: a child handle per device, each with a replica of the O(n) inputs.  vc_n2ll_batch
+// spreads the distinct thetas of a batch over the devices -- the GPU analogue of the reference's optimParallel
+// fan-out over PSOCK workers (R-pkg/R/SVC_mle.R:164-200); no collective, results are gathered on the host.
+extern "C" int vc_create_multi(vc_handle** out, const vc_config* cfg_in, int64_t n, int32_t d, int32_t p,
+                               int32_t q, const double* locs, const double* X, const double* W,
+                               const double* y, const int32_t* devices, int32_t ndev) {
+  if (!out) return VC_ERR_INVALID;
+  *out = nullptr;
+  if (!devices || ndev < 1 || ndev > 64) return vc_fail(nullptr, VC_ERR_INVALID, "device list must hold 1..64 ordinals");
+  vc_config cfg;
+  if (cfg_in) cfg = *cfg_in; else vc_config_default(&cfg);
+  vc_handle* h = new vc_handle();
+  h->cfg = cfg; h->n = n; h->d = d; h->p = p; h->q = q;
+  for (int i = 0; i < ndev; ++i) {
+    vc_config c = cfg;
+    c.device = devices[i];
+    vc_handle* k = nullptr;
+    const int rc = vc_create(&k, &c, n, d, p, q, locs, X, W, y);
+    if (rc != VC_OK) {                        // g_create_error already holds the child's message
+      vc_free_handle(h);
+      return rc;
+    }
+    h->kids.push_back(k);
+  }
+  h->device = devices[0];
+  h->n_pad = h->kids[0]->n_pad;
+  *out = h;
+  return VC_OK;
+}
+
+static int multi_batch(vc_handle* h, int32_t m, const double* thetas, int32_t mu_mode, const double* mus_in,
+                       double* out_n2ll, double* out_mu, int32_t* out_status) {
+  const int nth = 2 * h->q + 1, p = h->p;
+  const int G = (int)h->kids.size();
+  // distinct thetas, in order of first appearance; all evaluations of one theta go to the same device
+  std::vector<int> uniq, uniq_of(m);
+  for (int e = 0; e < m; ++e) {
+    int u = -1;
+    for (size_t k = 0; k < uniq.size() && u < 0; ++k)
+      if (memcmp(thetas + (size_t)uniq[k] * nth, thetas + (size_t)e * nth, nth * sizeof(double)) == 0) u = (int)k;
+    if (u < 0) { u = (int)uniq.size(); uniq.push_back(e); }
+    uniq_of[e] = u;
+  }
+  const int nu = (int)uniq.size();
+  // contiguous blocks of distinct thetas per device (neighbouring stencil points have similar cost)
+  std::vector<std::vector<int>> evals(G);
+  for (int e = 0; e < m; ++e) evals[(int)((int64_t)uniq_of[e] * G / nu)].push_back(e);
+  std::vector<int> rcs(G, VC_OK);
+  std::vector<std::vector<double>> th(G), mu(G), val(G), muo(G);
+  std::vector<std::vector<int32_t>> st(G);
+  std::vector<std::thread> workers;
+  for (int g = 0; g < G; ++g) {
+    const int mg = (int)evals[g].size();
+    if (mg == 0) continue;
+    th[g].resize((size_t)mg * nth); val[g].resize(mg); st[g].resize(mg); muo[g].resize((size_t)mg * p);
+    if (mus_in) mu[g].resize((size_t)mg * p);
+    for (int i = 0; i < mg; ++i) {
+      memcpy(&th[g][(size_t)i * nth], thetas + (size_t)evals[g][i] * nth, nth * sizeof(double));
+      if (mus_in) memcpy(&mu[g][(size_t)i * p], mus_in + (size_t)evals[g][i] * p, p * sizeof(double));
+    }
+    workers.emplace_back([&, g, mg]() {
+      rcs[g] = vc_n2ll_batch(h->kids[g], mg, th[g].data(), mu_mode, mus_in ? mu[g].data() : nullptr, val[g].data(),
+                             muo[g].data(), st[g].data());
+    });
+  }
+  for (auto& w : workers) w.join();
+  int first = VC_OK;
+  for (int g = 0; g < G; ++g) {
+    const int mg = (int)evals[g].size();
+    if (rcs[g] == VC_ERR_CUDA || rcs[g] == VC_ERR_OOM) return vc_fail(h, rcs[g], h->kids[g]->err);
+    for (int i = 0; i < mg; ++i) {
+      const int e = evals[g][i];
+      out_n2ll[e] = val[g][i];
+      if (out_mu) memcpy(out_mu + (size_t)e * p, &muo[g][(size_t)i * p], p * sizeof(double));
+      if (out_status) out_status[e] = st[g][i];
+    }
+    if (mg > 0 && evals[g].back() == m - 1) h->kid_last = g;
+  }
+  for (int e = 0; e < m && first == VC_OK; ++e) {          // first non-OK status in evaluation order
+    const int g = (int)((int64_t)uniq_of[e] * G / nu);
+    for (size_t i = 0; i < evals[g].size(); ++i)
+      if (evals[g][i] == e && st[g][i] != VC_OK) { first = st[g][i]; h->err = h->kids[g]->err; h->last_info = h->kids[g]->last_info; }
+  }
+  return first;
+}
+
 extern "C" int vc_set_data(vc_handle* h, const double* locs, const double* X, const double* W,
                            const double* y) {
   if (!h) return VC_ERR_INVALID;
+  if (!h->kids.empty()) {
+    for (vc_handle* k : h->kids) {
+      const int rc = vc_set_data(k, locs, X, W, y);
+      if (rc != VC_OK) return vc_fail(h, rc, k->err);
+    }
+    return VC_OK;
+  }
   try {
     VC_CUDA_TRY(cudaSetDevice(h->device));
     if (locs) upload_padded(h->locs, locs, h->n, h->n_pad, h->d, h->st_main);
@@ -315,6 +414,7 @@ extern "C" int vc_n2ll_batch(vc_handle* h, int32_t m, const double* thetas, int3
   if (m < 1 || !thetas || !out_n2ll) return vc_fail(h, VC_ERR_INVALID, "bad batch arguments");
   if (mu_mode != VC_MU_GLS && mu_mode != VC_MU_FIXED) return vc_fail(h, VC_ERR_INVALID, "unknown mu_mode");
   if (mu_mode == VC_MU_FIXED && !mus_in) return vc_fail(h, VC_ERR_INVALID, "mu_mode FIXED needs mu");
+  if (!h->kids.empty()) return multi_batch(h, m, thetas, mu_mode, mus_in, out_n2ll, out_mu, out_status);
   if (h->dist) {
     int first = VC_OK;
     for (int e = 0; e < m; ++e) {
@@ -463,6 +563,12 @@ extern "C" int vc_n2ll_batch(vc_handle* h, int32_t m, const double* thetas, int3
 extern "C" int vc_n2ll(vc_handle* h, const double* theta, int32_t mu_mode, const double* mu_in,
                        double* n2ll, double* mu_out, double* logdet, double* quad) {
   if (!h || !theta || !n2ll) return VC_ERR_INVALID;
+  if (!h->kids.empty()) {            // a lone evaluation runs on the child that holds the last factor (cache hits)
+    vc_handle* k = vc_target(h);
+    const int rc = vc_n2ll(k, theta, mu_mode, mu_in, n2ll, mu_out, logdet, quad);
+    if (rc != VC_OK) { h->err = k->err; h->last_info = k->last_info; }
+    return rc;
+  }
   if (h->dist) return vc_dist_n2ll(h, theta, mu_mode, mu_in, n2ll, mu_out, logdet, quad);
   int32_t status = VC_OK;
   h->last_info = 0;
@@ -477,6 +583,7 @@ extern "C" int vc_n2ll(vc_handle* h, const double* theta, int32_t mu_mode, const
 
 extern "C" int vc_sigma(vc_handle* h, const double* theta, double* out) {
   if (!h || !theta || !out) return VC_ERR_INVALID;
+  h = vc_target(h);
   if (h->dist) return vc_fail(h, VC_ERR_INVALID, "vc_sigma is not available on a distributed handle");
   VcTheta th;
   if (vc_make_theta(h, theta, &th) != VC_OK) return vc_fail(h, VC_ERR_INVALID, "invalid theta");
@@ -497,6 +604,7 @@ extern "C" int vc_sigma(vc_handle* h, const double* theta, double* out) {
 
 extern "C" int vc_sigma_device(vc_handle* h, const double* theta, double* out_dev) {
   if (!h || !theta || !out_dev) return VC_ERR_INVALID;
+  h = vc_target(h);
   if (h->dist) return vc_fail(h, VC_ERR_INVALID, "vc_sigma_device is not available on a distributed handle");
   VcTheta th;
   if (vc_make_theta(h, theta, &th) != VC_OK) return vc_fail(h, VC_ERR_INVALID, "invalid theta");
@@ -516,6 +624,7 @@ extern "C" int vc_sigma_device(vc_handle* h, const double* theta, double* out_de
 
 extern "C" int vc_get_chol(vc_handle* h, double* R_out) {
   if (!h || !R_out) return VC_ERR_INVALID;
+  h = vc_target(h);
   if (h->dist) return vc_fail(h, VC_ERR_INVALID, "vc_get_chol is not available on a distributed handle");
   if (!h->factor_valid) return vc_fail(h, VC_ERR_INVALID, "no valid factor: call vc_n2ll first");
   double* dev = nullptr;
@@ -535,6 +644,7 @@ extern "C" int vc_get_chol(vc_handle* h, double* R_out) {
 
 extern "C" int vc_get_whitened(vc_handle* h, double* Z_out) {
   if (!h || !Z_out) return VC_ERR_INVALID;
+  h = vc_target(h);
   if (h->dist) return vc_fail(h, VC_ERR_INVALID, "vc_get_whitened is not available on a distributed handle");
   if (!h->factor_valid) return vc_fail(h, VC_ERR_INVALID, "no valid factor: call vc_n2ll first");
   double* dev = nullptr;
@@ -555,10 +665,23 @@ extern "C" int vc_get_whitened(vc_handle* h, double* Z_out) {
 
 extern "C" int vc_timings(vc_handle* h, vc_timing* out) {
   if (!h || !out) return VC_ERR_INVALID;
+  h = vc_target(h);
   *out = h->last_timing;
   return VC_OK;
 }
-extern "C" int vc_last_info(vc_handle* h) { return h ? h->last_info : 0; }
-extern "C" const char* vc_last_error(vc_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+extern "C" int vc_last_info(vc_handle* h) {
+  if (!h) return 0;
+  return (!h->kids.empty() && h->last_info == 0) ? vc_target(h)->last_info : h->last_info;
+}
+extern "C" const char* vc_last_error(vc_handle* h) {
+  if (!h) return g_create_error.c_str();
+  return (!h->kids.empty() && h->err.empty()) ? vc_target(h)->err.c_str() : h->err.c_str();
+}
 extern "C" int64_t vc_padded_n(vc_handle* h) { return h ? h->n_pad : 0; }
-extern "C" int64_t vc_launch_count(vc_handle* h) { return h ? h->launches : 0; }
+extern "C" int64_t vc_launch_count(vc_handle* h) {
+  if (!h) return 0;
+  int64_t s = h->launches;
+  for (vc_handle* k : h->kids) s += k->launches;
+  return s;
+}
+extern "C" int32_t vc_device_count(vc_handle* h) { return h ? (h->kids.empty() ? 1 : (int32_t)h->kids.size()) : 0; }

@@ -313,6 +313,7 @@ int post_edof(vc_handle* h, const double* theta, const std::vector<double>& sigm
 
 extern "C" int vc_post(vc_handle* h, const double* theta, double* mu_gls, double* sigma_fe, double* edof) {
   if (!h || !theta) return VC_ERR_INVALID;
+  h = vc_target(h);
   if (h->dist) return vc_fail(h, VC_ERR_INVALID, "vc_post is not available on a distributed handle");
   const int p = h->p, m = p + 1;
   std::vector<double> mu(p);
@@ -338,6 +339,7 @@ extern "C" int vc_predict(vc_handle* h, const double* theta, const double* mu, i
                           const double* newlocs, const double* newX, const double* newW, double* eff,
                           double* y_pred, double* y_var) {
   if (!h || !theta || !mu || !newlocs || !eff || n_new < 1) return VC_ERR_INVALID;
+  h = vc_target(h);
   if (h->dist) return vc_fail(h, VC_ERR_INVALID, "vc_predict is not available on a distributed handle");
   if ((y_pred || y_var) && (!newX || !newW)) return vc_fail(h, VC_ERR_INVALID, "y_pred / y_var need newX and newW");
   const int p = h->p, q = h->q, d = h->d;

@@ -41,7 +41,12 @@ struct vc_handle {
   std::string err;
   // distributed state lives in vc_dist.cu
   void* dist = nullptr;
+  // multi-device handle (vc_create_multi): this object owns no device memory, only one child handle per device
+  std::vector<vc_handle*> kids;
+  int kid_last = 0;                  // child that ran the last evaluation of the last call
 };
+// the handle single-target entry points act on: the child holding the last evaluation, or h itself
+inline vc_handle* vc_target(vc_handle* h) { return (h && !h->kids.empty()) ? h->kids[h->kid_last] : h; }
 
 
 int vc_make_theta(const vc_handle* h, const double* theta, VcTheta* t);

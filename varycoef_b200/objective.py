@@ -83,11 +83,17 @@ class SVCObjective:
                 raise ValueError("length(theta) == 2L is not TRUE (tapering with %s needs q = 1)" % cov_name)
             cfg.taper_id = _lib.TAPER_IDS[tap]
             cfg.taper_range = float(tapering)
-        cfg.device = int(device)
+        devices = [int(v) for v in device] if isinstance(device, (list, tuple)) else None
+        cfg.device = devices[0] if devices else int(device)
         cfg.nb_outer = int(nb_outer)
         cfg.flags = (0 if lookahead else _lib.VC_FLAG_NO_LOOKAHEAD) | (_lib.VC_FLAG_LEGACY_SYRK if legacy_syrk else 0) | (_lib.VC_FLAG_LEGACY_POTRF if legacy_potrf else 0)
         self._cfg = cfg
-        if _dist_grid is None:
+        if devices is not None and _dist_grid is None:
+            # one replica per GPU; n2LL_batch spreads the stencil over them (optimParallel, SVC_mle.R:164-200)
+            dv = (C.c_int32 * len(devices))(*devices)
+            code = lib().vc_create_multi(C.byref(self._h), C.byref(cfg), n, self.d, self.p, self.q,
+                                         ptr(self.locs), ptr(self.X), ptr(self.W), ptr(self.y), dv, len(devices))
+        elif _dist_grid is None:
             code = lib().vc_create(C.byref(self._h), C.byref(cfg), n, self.d, self.p, self.q,
                                    ptr(self.locs), ptr(self.X), ptr(self.W), ptr(self.y))
         else:
@@ -239,6 +245,10 @@ class SVCObjective:
     @property
     def launch_count(self):
         return int(lib().vc_launch_count(self._h))
+
+    @property
+    def device_count(self):
+        return int(lib().vc_device_count(self._h))
 
     @property
     def padded_n(self):

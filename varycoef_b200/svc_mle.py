@@ -171,6 +171,11 @@ def SVC_mle(y, X, locs, W=None, control=None, optim_control=None, device=0, comp
     (the reference returns list(obj_fun, args), SVC_mle.R:111-132)."""
     control = SVC_mle_control() if control is None else dict(control)
     optim_control = dict(optim_control or {})
+    # control$parallel (SVC_mle.R:164-200: the optimParallel cluster) names the GPUs here: a list of device
+    # ordinals gives a multi-device objective whose batches (optim's stencils) are spread over them
+    if isinstance(control.get("parallel"), (list, tuple)) and len(control["parallel"]) > 0:
+        device = [int(v) for v in control["parallel"]]
+    dev0 = device[0] if isinstance(device, (list, tuple)) else int(device)
     y = np.asarray(y, dtype=np.float64).ravel()
     X = np.asarray(X, dtype=np.float64)
     if X.ndim == 1:
@@ -185,7 +190,7 @@ def SVC_mle(y, X, locs, W=None, control=None, optim_control=None, device=0, comp
     if control.get("lower") is None or control.get("upper") is None or control.get("init") is None:
         if control["tapering"] is None:
             med = median_dist(locs, control["dist"].get("method", "euclidean"),
-                              float(control["dist"].get("p", 2.0)))
+                              float(control["dist"].get("p", 2.0)), device=dev0)
         else:
             med = 1.0   # median(lower.tri(d@entries)) of a logical matrix (SVC_mle.R:44): always 1
         y_var = float(np.var(y, ddof=1))
