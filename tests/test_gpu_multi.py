@@ -86,6 +86,9 @@ def test_fit_on_a_multi_device_objective_matches_single_device_fit():
     devices = list(range(min(ng, 8))) if ng >= 2 else [0, 0]
     n, p = 900, 2
     locs, X, y = _synth(n, p, 4)
+    # spatially varying coefficients with real signal, so that the optimum is interior (a fit that ends at
+    # sigma^2 = 0 makes optimhess step to negative variances, where Sigma_y is not positive definite -- in R too)
+    y = (1.0 + np.sin(locs[:, 0] / 1.5)) + X[:, 1] * (2.0 + np.cos(locs[:, 1] / 2.0)) + 0.4 * np.random.default_rng(8).standard_normal(n)
     ctl = SVC_mle_control(profileLik=True, hessian=True)
     f1 = SVC_mle(y, X, locs, control=ctl, compute_edof=False)
     ctl2 = dict(ctl, parallel=devices)
