@@ -433,8 +433,12 @@ def sharded_record(args, dist, world, rank, local, peak_tf, single_c3):
     tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     dist.all_reduce(t, op=dist.ReduceOp.SUM)
     elapsed, launches = float(tmax[0]), int(t[1].item())
+    rx, bound = obj.dist_traffic()
     obj.close()
     chol_s = phase["chol_ms"] / Ks * 1e-3
+    rec.update({"nvlink_rx_bytes_per_rank": rx, "nvlink_rx_gbs_per_rank": rx / chol_s / 1e9,
+                "nvlink_note": "panel + L_DD broadcasts on the world communicator: every rank receives the whole panel "
+                               "(~4 n^2 B); a row/column-communicator scheme would need nvlink_bytes_per_rank_bound"})
     rec.update({"workload": desc, "n": n, "p": p, "q": p, "cov": cov, "steps": Ks, "warmup": Ws,
                 "evals_per_s": Ks / elapsed, "ms_per_eval": elapsed / Ks * 1e3, "scaling": "strong",
                 "tflops": n ** 3 / 3.0 / chol_s / 1e12, "peak_tflops": peak_tf * world,
@@ -442,7 +446,7 @@ def sharded_record(args, dist, world, rank, local, peak_tf, single_c3):
                 "peak_source": "N x fp64 DMMA probe of rank 0 (vc_probe_dmma_peak)",
                 "phases_ms": {k: v / Ks for k, v in phase.items()}, "gpu_launches": launches, "clocks": clocks,
                 "n2ll_sample": vals[:2],
-                "nvlink_bytes_per_rank_bound": 8.0 * n * n * (1.0 / pr + 1.0 / pc) / 2.0,
+                "nvlink_bytes_per_rank_bound": bound,
                 "parallelism": "2D block-cyclic Sigma_y, NCCL panel broadcasts, lookahead"})
     return rec
 

@@ -197,6 +197,10 @@ VC_API int vc_create_dist(vc_handle** h, const vc_config* cfg, int64_t n, int32_
                    const double* locs, const double* X, const double* W, const double* y,
                    int32_t rank, int32_t world, int32_t pr, int32_t pc, const char nccl_id[128]);
 
+/* NVLink bytes this rank receives per evaluation (panel + L_DD broadcasts on the world communicator), next to the
+ * n^2 8 (1/pr + 1/pc) / 2 a row / column-communicator scheme would need */
+VC_API int vc_dist_traffic(vc_handle* h, double* rx_bytes, double* rowcol_bound_bytes);
+
 /* host-only block-cyclic map (no GPU needed): owner rank and local tile index of 512-block (bi, bj) */
 VC_API int vc_bc_owner(int32_t bi, int32_t bj, int32_t pr, int32_t pc);
 VC_API int vc_bc_local(int32_t b, int32_t nprocs_dim);

@@ -81,6 +81,7 @@ SIGNATURES = {
     "vc_create_dist": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(VcConfig), C.c_int64, C.c_int32, C.c_int32,
                                  C.c_int32, _dp, _dp, _dp, _dp, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                  C.c_char_p]),
+    "vc_dist_traffic": (C.c_int, [C.c_void_p, _dp, _dp]),
     "vc_bc_owner": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "vc_bc_local": (C.c_int, [C.c_int32, C.c_int32]),
     "vc_bc_count": (C.c_int, [C.c_int32, C.c_int32, C.c_int32]),

@@ -147,6 +147,7 @@ struct VcDist {
   std::vector<DistStep> steps;
   double* dd = nullptr;       // nb tiles x (128 x nb*128) + nb x (128 x 128) inverses
   double* pnl[2] = {nullptr, nullptr};   // double-buffered gathered panel (lookahead)
+  double rx_bytes = 0.0;      // bytes this rank receives over NVLink per evaluation (panel + L_DD broadcasts)
   double* red = nullptr;      // [gram pairs*2 | logdet | quad(2)]
   int* info_red = nullptr;
 };
@@ -241,6 +242,11 @@ static void build_dist_plan(vc_handle* h, VcDist* D) {
       for (int t : tr) if ((t >> 16) >= ne) tiles.push_back(t);
       st.trailing_rest = span_end(off);
     }
+    // NVLink accounting: every broadcast this rank is not the root of delivers its payload here
+    if (D->world > 1) {
+      if (D->rank != st.diag_owner) D->rx_bytes += 8.0 * ((double)nb * VC_TILE * nb * VC_TILE + (double)nb * VC_TILE * VC_TILE);
+      for (const BcastOp& op : st.bcasts) if (op.root != D->rank) D->rx_bytes += 8.0 * (double)op.count;
+    }
     D->steps.push_back(st);
   }
   VC_CUDA_TRY(cudaMalloc(&D->tiles_dev, std::max<size_t>(tiles.size(), 1) * sizeof(int)));
@@ -324,6 +330,17 @@ extern "C" int vc_create_dist(vc_handle** out, const vc_config* cfg_in, int64_t 
     return vc_fail(nullptr, e.code, e.msg);
   }
   *out = h;
+  return VC_OK;
+}
+
+// bytes received over NVLink by this rank per evaluation, and the bound n^2 8 (1/pr + 1/pc) / 2 of a
+// row / column-communicator scheme for comparison
+extern "C" int vc_dist_traffic(vc_handle* h, double* rx_bytes, double* rowcol_bound_bytes) {
+  if (!h || !h->dist) return VC_ERR_INVALID;
+  VcDist* D = (VcDist*)h->dist;
+  if (rx_bytes) *rx_bytes = D->rx_bytes;
+  if (rowcol_bound_bytes)
+    *rowcol_bound_bytes = D->world > 1 ? 8.0 * (double)h->n_pad * (double)h->n_pad * (1.0 / D->pr + 1.0 / D->pc) / 2.0 : 0.0;
   return VC_OK;
 }
 
@@ -446,18 +463,36 @@ int vc_dist_n2ll(vc_handle* h, const double* theta, int32_t mu_mode, const doubl
         VC_CUDA_TRY(cudaStreamWaitEvent(sp, h->cw.ev_col, 0));
       }
       const int rest = s.trailing_rest.n;
-      // A persistent update kernel never yields an SM, so the rest update leaves R SMs to the panel
-      // stream (potrf chain, the column ranks' TRSM + inner updates, NCCL's kernels).  Measured at
-      // n = 150 000 on 8 GPUs (4x2): R = 8 -> 4.70 s, R = 16 -> 4.55 s per evaluation; the per-rank
-      // cost model of the single-GPU driver did worse (5.7 s): every rank is slowed to the pace of
-      // the slowest one at each panel broadcast, so a uniform R wins.  VC_DIST_RESERVE overrides.
-      int reserve = 0;
+      // A persistent update kernel never yields an SM, so the part of the rest update that runs BESIDE the
+      // panel phase of step i + 1 (potrf chain, the column ranks' TRSM + inner updates, NCCL's kernels, all on
+      // sp) leaves R SMs free.  Only that part: the rest update is cut in two, part B first on every SM (the
+      // panel kernels queue behind it), then part A on num_sms - R CTAs with the panel beside it.  A is sized
+      // from an estimate of the panel phase (uniform over the ranks: they meet at every broadcast anyway).
+      // Neither part waits for the panel, so a late broadcast never idles the update.  Round 1 reserved R = 16
+      // for the WHOLE rest update (10.8 % of the DMMA pipes).  VC_DIST_RESERVE / VC_DIST_SPLIT=0 override.
+      int reserve = 0, nA = rest;
       if (la && !h->cw.legacy_syrk && i + 1 < nsteps) {
         static const int fixed = getenv("VC_DIST_RESERVE") ? atoi(getenv("VC_DIST_RESERVE")) : 16;
-        reserve = std::min(fixed, h->cw.num_sms / 2);
+        static const bool split = !(getenv("VC_DIST_SPLIT") && atoi(getenv("VC_DIST_SPLIT")) == 0);
+        static const double safety = getenv("VC_DIST_SAFETY") ? atof(getenv("VC_DIST_SAFETY")) : 1.3;
+        reserve = std::max(1, std::min(fixed, h->cw.num_sms / 2));
+        if (split) {
+          const DistStep& nx = D->steps[i + 1];
+          const int nsub = nx.oe - nx.ob;
+          const int rows_max = (nt + D->nbt - nx.oe + D->pr - 1) / D->pr + 1;       // row tiles of the busiest column rank
+          const double t_diag = nsub * (45.0 + 2.0 * 20.0) + 0.5 * nsub * nsub * 20.0;   // us: potrf / TRSM / inner chain of L_DD
+          const double t_rows = (double)rows_max * (nsub + 0.5 * nsub * (nsub - 1)) * 20.0 / reserve;
+          const double t_bcast = 400.0 + 8.0 * rows_max * VC_TILE * (double)nsub * VC_TILE * D->pr / 300e3;   // us at ~300 GB/s
+          const double t_panel = t_diag + t_rows + t_bcast;
+          const double t_tile = 17.3 * (Kb / VC_TILE);
+          const int64_t want = (int64_t)(safety * t_panel / t_tile + 1.0) * (h->cw.num_sms - reserve);
+          nA = (int)std::min<int64_t>(rest, want);
+        }
       }
-      g.tiles = D->tiles_dev + s.trailing_rest.off; g.ntiles = rest;
-      vc_launch_syrk(g, h->cw.num_sms - reserve, h->cw.legacy_syrk, sm, &h->launches);
+      g.tiles = D->tiles_dev + s.trailing_rest.off; g.ntiles = rest - nA;
+      vc_launch_syrk(g, h->cw.num_sms, h->cw.legacy_syrk, sm, &h->launches);                  // part B: every SM
+      g.tiles = D->tiles_dev + s.trailing_rest.off + (rest - nA); g.ntiles = nA;
+      vc_launch_syrk(g, h->cw.num_sms - reserve, h->cw.legacy_syrk, sm, &h->launches);        // part A: beside the panel
       if (i + 1 < nsteps) {
         panel_phase(i + 1);
         if (la) VC_CUDA_TRY(cudaEventRecord(h->cw.ev_panel, sp));

@@ -246,6 +246,12 @@ class SVCObjective:
     def launch_count(self):
         return int(lib().vc_launch_count(self._h))
 
+    def dist_traffic(self):
+        """(bytes received over NVLink per evaluation by this rank, row/column-communicator bound); sharded handles."""
+        a, b = C.c_double(), C.c_double()
+        check(lib().vc_dist_traffic(self._h, C.byref(a), C.byref(b)), self._h)
+        return a.value, b.value
+
     @property
     def device_count(self):
         return int(lib().vc_device_count(self._h))
