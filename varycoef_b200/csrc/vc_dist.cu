@@ -133,7 +133,7 @@ struct DistStep {
   Span rows;                             // local row tiles >= oe (+ border), packed I
   std::vector<Span> inner;               // per sub-panel: (I in rows) x (J in (jt, oe))
   std::vector<BcastOp> bcasts;           // panel blocks, in doubles relative to pnl
-  Span trailing_col, trailing_rest;      // next block's columns first (lookahead), then the rest
+  Span trailing_cold, trailing_col, trailing_rest;   // next diagonal block, the rest of the next block's columns, the rest
 };
 struct VcDist {
   int rank = 0, world = 1, pr = 1, pc = 1, my_pr = 0, my_pc = 0;
@@ -147,6 +147,7 @@ struct VcDist {
   std::vector<DistStep> steps;
   double* dd = nullptr;       // nb tiles x (128 x nb*128) + nb x (128 x 128) inverses
   double* pnl[2] = {nullptr, nullptr};   // double-buffered gathered panel (lookahead)
+  cudaEvent_t ev_dd = nullptr, ev_rows = nullptr;   // L_DD has arrived / the panel rows are packed
   double rx_bytes = 0.0;      // bytes this rank receives over NVLink per evaluation (panel + L_DD broadcasts)
   double* red = nullptr;      // [gram pairs*2 | logdet | quad(2)]
   int* info_red = nullptr;
@@ -158,6 +159,8 @@ void vc_dist_destroy(vc_handle* h) {
   VcDist* D = (VcDist*)h->dist;
   if (!D) return;
   if (D->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(D->comm);
+  if (D->ev_dd) cudaEventDestroy(D->ev_dd);
+  if (D->ev_rows) cudaEventDestroy(D->ev_rows);
   cudaFree(D->col_tiles_dev); cudaFree(D->tiles_dev); cudaFree(D->dd); cudaFree(D->pnl[0]); cudaFree(D->pnl[1]);
   cudaFree(D->red); cudaFree(D->info_red);
   delete D;
@@ -236,7 +239,10 @@ static void build_dist_plan(vc_handle* h, VcDist* D) {
       if (st.oe < nt) trailing_tiles(nt, nbt, nb, pr, pc, D->rank, st.oe, tr);
       const int ne = std::min(st.oe + nb, nt);
       int64_t off = span_begin();
-      for (int t : tr) if ((t >> 16) < ne) tiles.push_back(t);
+      for (int t : tr) if ((t >> 16) < ne && (t & 0xffff) < ne) tiles.push_back(t);    // the next diagonal block
+      st.trailing_cold = span_end(off);
+      off = span_begin();
+      for (int t : tr) if ((t >> 16) < ne && (t & 0xffff) >= ne) tiles.push_back(t);
       st.trailing_col = span_end(off);
       off = span_begin();
       for (int t : tr) if ((t >> 16) >= ne) tiles.push_back(t);
@@ -373,23 +379,34 @@ int vc_dist_n2ll(vc_handle* h, const double* theta, int32_t mu_mode, const doubl
     base.a = h->M.a; base.cb = h->M.cb; base.b = h->M.b; base.ldb = h->M.ldb; base.nt = nt;
     base.blk = nb; base.pr = D->pr; base.pc = D->pc;
     base.nbatch = 1;
-    // Lookahead: the panel phase of block s+1 (factor / broadcasts / solves, stream sp) overlaps the
-    // "rest" part of the trailing update of block s (stream sm).  All NCCL calls are on sp, in the
-    // same order on every rank.  A persistent update kernel never yields an SM, so the rest update
-    // leaves a few SMs to the panel stream and to NCCL's own kernels.
+    // Schedule of one outer block (lookahead; sm = main stream, sp = high-priority panel stream):
+    //   sm: colD(s)  | colR(s) on num_sms - Rd ............ | rows(s+1) at FULL width | rest(s): part A on num_sms - Rn, part B on all
+    //   sp:          '-> diag(s+1): L_DD chain, NCCL bcast -^             '-> NCCL panel broadcast(s+1), beside part A
+    //  colD  update of the NEXT diagonal block only (its owner), so that its factorisation starts at once
+    //  diag  owner factors L_DD (potrf / TRSM / inner updates on <= Rd SMs) and broadcasts it with the tile inverses
+    //  rows  the ranks of the panel's process column solve their row tiles against L_DD (TRSM + inner updates)
+    //        -- on EVERY SM, not on a reserved handful as in round 1 -- and pack their part of the panel
+    //  rest  the trailing update; only the NCCL kernels of the panel broadcast need SMs beside it, and only for
+    //        its first part (A); part B follows on all SMs and waits for nothing.
+    // All NCCL calls are on sp, in the same order on every rank; panel buffers are double-buffered.
     const bool la = h->cw.lookahead;
     cudaStream_t sm = st, sp = la ? h->st_panel : st;
     if (la) {
       VC_CUDA_TRY(cudaEventRecord(h->cw.ev_update, sm));
       VC_CUDA_TRY(cudaStreamWaitEvent(sp, h->cw.ev_update, 0));
     }
+    if (!D->ev_dd) {
+      VC_CUDA_TRY(cudaEventCreateWithFlags(&D->ev_dd, cudaEventDisableTiming));
+      VC_CUDA_TRY(cudaEventCreateWithFlags(&D->ev_rows, cudaEventDisableTiming));
+    }
+    static const int Rd = getenv("VC_DIST_RESERVE_DIAG") ? atoi(getenv("VC_DIST_RESERVE_DIAG")) : 8;
+    static const int Rn = getenv("VC_DIST_RESERVE") ? atoi(getenv("VC_DIST_RESERVE")) : 8;
+    static const double safety = getenv("VC_DIST_SAFETY") ? atof(getenv("VC_DIST_SAFETY")) : 1.5;
     double* dd_linv = D->dd + (size_t)nb * VC_TILE * ((size_t)nb * VC_TILE);
-    // panel phase of step i (stream sp): diagonal block, L_DD broadcast, column solves, panel broadcast
-    auto panel_phase = [&](size_t i) {
+    // diagonal block of step i on stream q: factor (owner), broadcast L_DD + inverses
+    auto panel_diag = [&](size_t i, cudaStream_t q) {
       const DistStep& s = D->steps[i];
-      const int nsub = s.oe - s.ob;
-      const int Kb = nsub * VC_TILE;
-      double* pnl = D->pnl[i & 1];
+      const int Kb = (s.oe - s.ob) * VC_TILE;
       if (D->rank == s.diag_owner) {
         for (int jt = s.ob; jt < s.oe; ++jt) {
           const int k = jt - s.ob;
@@ -397,106 +414,126 @@ int vc_dist_n2ll(vc_handle* h, const double* theta, int32_t mu_mode, const doubl
           double* diag = vc_host_tile_ptr(h->M, loc_tile_h(jt, nb, D->pr), loc_tile_h(jt, nb, D->pc), &ldd);
           // potrf indexes its inverse slot by jt: bias the base so that slot jt is dd_linv[jt - ob]
           vc_launch_potrf(diag, ldd, jt, dd_linv - (int64_t)s.ob * VC_TILE * VC_TILE, h->cw.logdet_part,
-                          h->cw.info, h->cw.legacy_potrf, sp, &h->launches);
+                          h->cw.info, h->cw.legacy_potrf, q, &h->launches);
           VcGemmArgs g = base;
           g.linv = dd_linv + (size_t)k * VC_TILE * VC_TILE;
           g.jt = jt; g.K = VC_TILE;
           g.k0 = loc_tile_h(jt, nb, D->pc) * VC_TILE;
           g.tiles = D->tiles_dev + s.d_trsm[k].off; g.ntiles = s.d_trsm[k].n;
-          vc_launch_trsm(g, g.ntiles, sp, &h->launches);
+          vc_launch_trsm(g, g.ntiles, q, &h->launches);
           g.tiles = D->tiles_dev + s.d_inner[k].off; g.ntiles = s.d_inner[k].n;
-          vc_launch_syrk(g, h->cw.num_sms, h->cw.legacy_syrk, sp, &h->launches);
+          vc_launch_syrk(g, h->cw.num_sms, h->cw.legacy_syrk, q, &h->launches);
         }
         vc_launch_pack_tiles(base, D->tiles_dev + s.d_pack.off, s.d_pack.n,
-                             loc_tile_h(s.ob, nb, D->pc) * VC_TILE, Kb, D->dd, s.ob, sp, &h->launches);
+                             loc_tile_h(s.ob, nb, D->pc) * VC_TILE, Kb, D->dd, s.ob, q, &h->launches);
       }
       if (D->world > 1)
         VC_NCCL_TRY(g_nccl.Broadcast(D->dd, D->dd, (size_t)nb * VC_TILE * ((size_t)nb * VC_TILE) +
                                                        (size_t)nb * VC_TILE * VC_TILE,
-                                     ncclFloat64_, s.diag_owner, D->comm, sp));
-      if (D->my_pc == s.pcp && s.rows.n > 0) {
-        for (int jt = s.ob; jt < s.oe; ++jt) {
-          const int k = jt - s.ob;
-          VcGemmArgs g = base;
-          g.linv = dd_linv + (size_t)k * VC_TILE * VC_TILE;
-          g.jt = jt; g.K = VC_TILE;
-          g.k0 = loc_tile_h(jt, nb, D->pc) * VC_TILE;
-          g.tiles = D->tiles_dev + s.rows.off; g.ntiles = s.rows.n;
-          vc_launch_trsm(g, g.ntiles, sp, &h->launches);
-          g.tiles = D->tiles_dev + s.inner[k].off; g.ntiles = s.inner[k].n;
-          g.src_b.pnl = D->dd; g.src_b.ld = VC_TILE; g.src_b.tile_stride = (int64_t)VC_TILE * Kb;
-          g.src_b.tile0 = s.ob; g.src_b.col0 = k * VC_TILE;
-          vc_launch_syrk(g, h->cw.num_sms, h->cw.legacy_syrk, sp, &h->launches);
-        }
-        vc_launch_pack_tiles(base, D->tiles_dev + s.rows.off, s.rows.n,
-                             loc_tile_h(s.ob, nb, D->pc) * VC_TILE, Kb, pnl, s.oe, sp, &h->launches);
+                                     ncclFloat64_, s.diag_owner, D->comm, q));
+    };
+    // row tiles of the panel of step i on stream q: solve against L_DD, pack
+    auto panel_rows = [&](size_t i, cudaStream_t q) {
+      const DistStep& s = D->steps[i];
+      const int Kb = (s.oe - s.ob) * VC_TILE;
+      if (D->my_pc != s.pcp || s.rows.n <= 0) return;
+      for (int jt = s.ob; jt < s.oe; ++jt) {
+        const int k = jt - s.ob;
+        VcGemmArgs g = base;
+        g.linv = dd_linv + (size_t)k * VC_TILE * VC_TILE;
+        g.jt = jt; g.K = VC_TILE;
+        g.k0 = loc_tile_h(jt, nb, D->pc) * VC_TILE;
+        g.tiles = D->tiles_dev + s.rows.off; g.ntiles = s.rows.n;
+        vc_launch_trsm(g, g.ntiles, q, &h->launches);
+        g.tiles = D->tiles_dev + s.inner[k].off; g.ntiles = s.inner[k].n;
+        g.src_b.pnl = D->dd; g.src_b.ld = VC_TILE; g.src_b.tile_stride = (int64_t)VC_TILE * Kb;
+        g.src_b.tile0 = s.ob; g.src_b.col0 = k * VC_TILE;
+        vc_launch_syrk(g, h->cw.num_sms, h->cw.legacy_syrk, q, &h->launches);
       }
+      vc_launch_pack_tiles(base, D->tiles_dev + s.rows.off, s.rows.n,
+                           loc_tile_h(s.ob, nb, D->pc) * VC_TILE, Kb, D->pnl[i & 1], s.oe, q, &h->launches);
+    };
+    // every distribution block of the panel of step i goes from its owner to all ranks (stream q)
+    auto panel_bcast = [&](size_t i, cudaStream_t q) {
+      const DistStep& s = D->steps[i];
+      double* pnl = D->pnl[i & 1];
       if (s.oe < nt && D->world > 1) {
         VC_NCCL_TRY(g_nccl.GroupStart());
         for (const BcastOp& op : s.bcasts)
           VC_NCCL_TRY(g_nccl.Broadcast(pnl + op.off, pnl + op.off, (size_t)op.count, ncclFloat64_, op.root,
-                                       D->comm, sp));
+                                       D->comm, q));
         VC_NCCL_TRY(g_nccl.GroupEnd());
       }
     };
-    // Lookahead, software-pipelined as in the single-GPU driver:
-    //   sm:  col(s) | rest A(s) on num_sms - R CTAs ...................... | rest B(s) on every SM | col(s+1)
-    //   sp:          panel phase (s+1): factor, NCCL broadcasts, solves ---^
-    // All NCCL calls are on sp, in the same order on every rank; the panel buffers are double-buffered.
+    // whole panel of step i: diag on sp, rows on sm (they wait for L_DD), broadcast on sp (waits for the pack)
+    auto panel = [&](size_t i) {
+      panel_diag(i, sp);
+      if (la) {
+        VC_CUDA_TRY(cudaEventRecord(D->ev_dd, sp));
+        VC_CUDA_TRY(cudaStreamWaitEvent(sm, D->ev_dd, 0));
+      }
+      panel_rows(i, sm);
+      if (la) {
+        VC_CUDA_TRY(cudaEventRecord(D->ev_rows, sm));
+        VC_CUDA_TRY(cudaStreamWaitEvent(sp, D->ev_rows, 0));
+      }
+      panel_bcast(i, sp);
+      if (la) VC_CUDA_TRY(cudaEventRecord(h->cw.ev_panel, sp));
+    };
+    auto update = [&](const VcGemmArgs& g0, const Span& sp_, int first, int count, int sms) {
+      if (count <= 0) return;
+      VcGemmArgs g = g0;
+      g.tiles = D->tiles_dev + sp_.off + first; g.ntiles = count;
+      vc_launch_syrk(g, sms, h->cw.legacy_syrk, sm, &h->launches);
+    };
     const size_t nsteps = D->steps.size();
-    panel_phase(0);
-    if (la) VC_CUDA_TRY(cudaEventRecord(h->cw.ev_panel, sp));
+    const int nsm = h->cw.num_sms;
+    panel(0);
     for (size_t i = 0; i < nsteps; ++i) {
       const DistStep& s = D->steps[i];
       if (s.oe >= nt) break;
       const int Kb = (s.oe - s.ob) * VC_TILE;
-      if (la) VC_CUDA_TRY(cudaStreamWaitEvent(sm, h->cw.ev_panel, 0));
+      if (la) VC_CUDA_TRY(cudaStreamWaitEvent(sm, h->cw.ev_panel, 0));       // panel i has arrived everywhere
       VcGemmArgs g = base;
       g.K = Kb;
       g.src_a.pnl = D->pnl[i & 1]; g.src_a.ld = VC_TILE; g.src_a.tile_stride = (int64_t)VC_TILE * Kb;
       g.src_a.tile0 = s.oe; g.src_a.col0 = 0;
       g.src_b = g.src_a;
-      g.tiles = D->tiles_dev + s.trailing_col.off; g.ntiles = s.trailing_col.n;
-      vc_launch_syrk(g, h->cw.num_sms, h->cw.legacy_syrk, sm, &h->launches);
+      const bool more = i + 1 < nsteps;
+      const bool ws = la && !h->cw.legacy_syrk;
+      update(g, s.trailing_cold, 0, s.trailing_cold.n, nsm);                  // colD: the next diagonal block
       if (la) {
         VC_CUDA_TRY(cudaEventRecord(h->cw.ev_col, sm));
         VC_CUDA_TRY(cudaStreamWaitEvent(sp, h->cw.ev_col, 0));
       }
-      const int rest = s.trailing_rest.n;
-      // A persistent update kernel never yields an SM, so the part of the rest update that runs BESIDE the
-      // panel phase of step i + 1 (potrf chain, the column ranks' TRSM + inner updates, NCCL's kernels, all on
-      // sp) leaves R SMs free.  Only that part: the rest update is cut in two, part B first on every SM (the
-      // panel kernels queue behind it), then part A on num_sms - R CTAs with the panel beside it.  A is sized
-      // from an estimate of the panel phase (uniform over the ranks: they meet at every broadcast anyway).
-      // Neither part waits for the panel, so a late broadcast never idles the update.  Round 1 reserved R = 16
-      // for the WHOLE rest update (10.8 % of the DMMA pipes).  VC_DIST_RESERVE / VC_DIST_SPLIT=0 override.
-      int reserve = 0, nA = rest;
-      if (la && !h->cw.legacy_syrk && i + 1 < nsteps) {
-        static const int fixed = getenv("VC_DIST_RESERVE") ? atoi(getenv("VC_DIST_RESERVE")) : 16;
-        static const bool split = !(getenv("VC_DIST_SPLIT") && atoi(getenv("VC_DIST_SPLIT")) == 0);
-        static const double safety = getenv("VC_DIST_SAFETY") ? atof(getenv("VC_DIST_SAFETY")) : 1.3;
-        reserve = std::max(1, std::min(fixed, h->cw.num_sms / 2));
-        if (split) {
-          const DistStep& nx = D->steps[i + 1];
-          const int nsub = nx.oe - nx.ob;
-          const int rows_max = (nt + D->nbt - nx.oe + D->pr - 1) / D->pr + 1;       // row tiles of the busiest column rank
-          const double t_diag = nsub * (45.0 + 2.0 * 20.0) + 0.5 * nsub * nsub * 20.0;   // us: potrf / TRSM / inner chain of L_DD
-          const double t_rows = (double)rows_max * (nsub + 0.5 * nsub * (nsub - 1)) * 20.0 / reserve;
-          const double t_bcast = 400.0 + 8.0 * rows_max * VC_TILE * (double)nsub * VC_TILE * D->pr / 300e3;   // us at ~300 GB/s
-          const double t_panel = t_diag + t_rows + t_bcast;
-          const double t_tile = 17.3 * (Kb / VC_TILE);
-          const int64_t want = (int64_t)(safety * t_panel / t_tile + 1.0) * (h->cw.num_sms - reserve);
-          nA = (int)std::min<int64_t>(rest, want);
-        }
+      if (more) {
+        panel_diag(i + 1, sp);
+        if (la) VC_CUDA_TRY(cudaEventRecord(D->ev_dd, sp));
       }
-      g.tiles = D->tiles_dev + s.trailing_rest.off; g.ntiles = rest - nA;
-      vc_launch_syrk(g, h->cw.num_sms, h->cw.legacy_syrk, sm, &h->launches);                  // part B: every SM
-      g.tiles = D->tiles_dev + s.trailing_rest.off + (rest - nA); g.ntiles = nA;
-      vc_launch_syrk(g, h->cw.num_sms - reserve, h->cw.legacy_syrk, sm, &h->launches);        // part A: beside the panel
-      if (i + 1 < nsteps) {
-        panel_phase(i + 1);
+      update(g, s.trailing_col, 0, s.trailing_col.n, nsm - (ws && more ? std::min(Rd, nsm / 2) : 0));   // colR
+      if (more) {
+        if (la) VC_CUDA_TRY(cudaStreamWaitEvent(sm, D->ev_dd, 0));
+        panel_rows(i + 1, sm);
+        if (la) {
+          VC_CUDA_TRY(cudaEventRecord(D->ev_rows, sm));
+          VC_CUDA_TRY(cudaStreamWaitEvent(sp, D->ev_rows, 0));
+        }
+        panel_bcast(i + 1, sp);
         if (la) VC_CUDA_TRY(cudaEventRecord(h->cw.ev_panel, sp));
       }
+      // rest(s): part A beside the NCCL broadcast of panel s+1 (sized from an estimate of its duration), part B on all SMs
+      const int rest = s.trailing_rest.n;
+      int nA = 0;
+      const int reserve = std::max(0, std::min(Rn, nsm / 2));
+      if (ws && more && D->world > 1 && reserve > 0) {
+        const DistStep& nx = D->steps[i + 1];
+        const double bytes = 8.0 * (double)(nt + D->nbt - nx.oe) * VC_TILE * (double)(nx.oe - nx.ob) * VC_TILE;
+        const double t_bcast = 300.0 + bytes / 150e3 + 40.0 * (double)nx.bcasts.size();   // us: ~150 GB/s + per-broadcast latency
+        const double t_tile = 17.3 * (Kb / VC_TILE);
+        nA = (int)std::min<int64_t>(rest, (int64_t)(safety * t_bcast / t_tile + 1.0) * (nsm - reserve));
+      }
+      update(g, s.trailing_rest, 0, nA, nsm - reserve);
+      update(g, s.trailing_rest, nA, rest - nA, nsm);
     }
     if (la) VC_CUDA_TRY(cudaStreamWaitEvent(sm, h->cw.ev_panel, 0));
     VC_CUDA_TRY(cudaEventRecord(h->ev[2], st));
