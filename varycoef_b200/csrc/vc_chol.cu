@@ -119,7 +119,7 @@ __device__ __forceinline__ const double* op_ptr(const GemmArgs& p, const VcOpSrc
                                                 int64_t& ld) {
   if (s.pnl) {
     ld = s.ld;
-    return s.pnl + (int64_t)(I - s.tile0) * s.tile_stride + (int64_t)(s.col0 + kcol) * s.ld;
+    return s.pnl + (int64_t)vc_panel_pos(s.map, I, s.tile0) * s.tile_stride + (int64_t)(s.col0 + kcol) * s.ld;
   }
   return row_tile_ptr(p, e, I, (int64_t)p.k0 + kcol, ld);
 }
@@ -1167,11 +1167,11 @@ k_potrf128c(double* At, int64_t lda, int jt, double* linv_all, double* logdet_pa
 // copy K panel columns (local column lcol0..) of the listed row tiles into a tile-major buffer:
 // tile I -> dst + (I - tile0) * 128 * K, column-major inside with ld 128 (distributed driver)
 __global__ void __launch_bounds__(256) k_pack_tiles(GemmArgs p, const int* __restrict__ tiles, int lcol0, int K,
-                                                    double* __restrict__ dst, int tile0) {
+                                                    double* __restrict__ dst, int tile0, VcPanelMap map) {
   const int I = tiles[blockIdx.x] & 0xffff;
   int64_t ld;
   const double* src = row_tile_ptr(p, 0, I, lcol0, ld);
-  double* d = dst + (int64_t)(I - tile0) * TILE * K;
+  double* d = dst + (int64_t)vc_panel_pos(map, I, tile0) * TILE * K;
   for (int idx = threadIdx.x; idx < (TILE / 2) * K; idx += blockDim.x) {
     const int r2 = idx % (TILE / 2), c = idx / (TILE / 2);
     *reinterpret_cast<double2*>(d + (int64_t)c * TILE + 2 * r2) =
@@ -1418,9 +1418,11 @@ void vc_launch_reset_info(int* info, cudaStream_t st, int64_t* launches, int nba
   ++*launches;
 }
 void vc_launch_pack_tiles(const VcGemmArgs& g, const int* tiles, int ntiles, int lcol0, int K, double* dst,
-                          int tile0, cudaStream_t st, int64_t* launches) {
+                          int tile0, cudaStream_t st, int64_t* launches, const VcPanelMap* map) {
   if (ntiles <= 0) return;
-  k_pack_tiles<<<ntiles, 256, 0, st>>>(g, tiles, lcol0, K, dst, tile0);
+  VcPanelMap m{};
+  if (map) m = *map;
+  k_pack_tiles<<<ntiles, 256, 0, st>>>(g, tiles, lcol0, K, dst, tile0, m);
   ++*launches;
 }
 void vc_append_trapezoid(std::vector<int>& out, int J0, int J1, int nrows) { append_trapezoid(out, J0, J1, nrows); }

@@ -119,12 +119,35 @@ void vc_launch_border_dist(double* b, int64_t ldb, int64_t n_pad, int p, const d
                            int64_t* launches);
 
 // vc_chol.cu
+// Order of the row tiles inside a gathered panel buffer of the sharded path: OWNER-major -- the tiles of
+// process row 0 first (then its border tiles), then process row 1, ... -- so that every owner's part is one
+// contiguous range and travels in ONE broadcast (round 1: tile order, one broadcast per distribution block,
+// 147 latency-bound NCCL operations per outer block at n = 150 000).
+struct VcPanelMap {
+  int pr;                 // process rows; 0 = plain tile order (position = I - tile0)
+  int nb, nt;             // tiles per distribution block, main row tiles
+  int main0;              // main tiles of process row 0 in the buffer (its border tiles follow them)
+  int chunk_off[8];       // first position of every process row's part
+  int bfirst[8];          // first distribution block of every process row that is in the buffer
+};
+#if defined(__CUDACC__)
+__host__ __device__ __forceinline__
+#else
+inline
+#endif
+int vc_panel_pos(const VcPanelMap& m, int I, int tile0) {
+  if (m.pr == 0) return I - tile0;
+  if (I >= m.nt) return m.chunk_off[0] + m.main0 + (I - m.nt);
+  const int B = I / m.nb, r = B % m.pr;
+  return m.chunk_off[r] + ((B - m.bfirst[r]) / m.pr) * m.nb + (I - B * m.nb);
+}
 struct VcOpSrc {          // where a GEMM operand row tile comes from
-  const double* pnl;      // gathered panel buffer (tile-major), or nullptr = the matrix itself at column k0
+  const double* pnl;      // gathered panel buffer, or nullptr = the matrix itself at column k0
   int64_t ld;             // leading dimension inside a tile of the buffer
   int64_t tile_stride;    // doubles between consecutive row tiles of the buffer
-  int tile0;              // global row tile stored at the start of the buffer
+  int tile0;              // global row tile stored at the start of the buffer (plain order)
   int col0;               // first panel column inside the buffer
+  VcPanelMap map;         // position of a row tile in the buffer
 };
 struct VcGemmArgs {       // by-value argument block of k_trsm_panel / k_syrk_ws / k_syrk_tiles
   double* a;              // (local) matrix, row tiles 0 .. nt-1 (global numbering)
@@ -192,7 +215,7 @@ void vc_launch_trsm(const VcGemmArgs& g, int grid, cudaStream_t st, int64_t* lau
 void vc_launch_syrk(const VcGemmArgs& g, int num_sms, bool legacy, cudaStream_t st, int64_t* launches);
 void vc_launch_reset_info(int* info, cudaStream_t st, int64_t* launches, int nbatch = 1);
 void vc_launch_pack_tiles(const VcGemmArgs& g, const int* tiles, int ntiles, int lcol0, int K, double* dst,
-                          int tile0, cudaStream_t st, int64_t* launches);
+                          int tile0, cudaStream_t st, int64_t* launches, const VcPanelMap* map = nullptr);
 void vc_append_trapezoid(std::vector<int>& out, int J0, int J1, int nrows);
 int vc_pick_reserved_sms(int num_sms, int rows_t, int nb, int rest_tiles, int* tiles_beside_panel, int nbatch = 1);
 

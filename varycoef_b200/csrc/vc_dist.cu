@@ -132,7 +132,8 @@ struct DistStep {
   // panel-column ranks
   Span rows;                             // local row tiles >= oe (+ border), packed I
   std::vector<Span> inner;               // per sub-panel: (I in rows) x (J in (jt, oe))
-  std::vector<BcastOp> bcasts;           // panel blocks, in doubles relative to pnl
+  std::vector<BcastOp> bcasts;           // one per process row: its part of the panel, in doubles relative to pnl
+  VcPanelMap map;                        // owner-major order of the row tiles >= oe in the panel buffer
   Span trailing_cold, trailing_col, trailing_rest;   // next diagonal block, the rest of the next block's columns, the rest
 };
 struct VcDist {
@@ -218,21 +219,31 @@ static void build_dist_plan(vc_handle* h, VcDist* D) {
         st.inner.push_back(span_end(off));
       }
     }
-    // panel broadcasts: every distribution block of rows >= oe, then the border
-    for (int B = st.oe / nb + (st.oe % nb ? 1 : 0); B < nblocks; ++B) {
-      const int t0 = B * nb, t1 = std::min(t0 + nb, nt);
-      BcastOp op;
-      op.off = (int64_t)(t0 - st.oe) * VC_TILE * Kb;
-      op.count = (int64_t)(t1 - t0) * VC_TILE * Kb;
-      op.root = (B % pr) * pc + st.pcp;
-      st.bcasts.push_back(op);
-    }
-    if (st.oe < nt) {
-      BcastOp op;
-      op.off = (int64_t)(nt - st.oe) * VC_TILE * Kb;
-      op.count = (int64_t)nbt * VC_TILE * Kb;
-      op.root = 0 * pc + st.pcp;
-      st.bcasts.push_back(op);
+    // the gathered panel buffer holds the row tiles >= oe in OWNER-major order (VcPanelMap); every process row's
+    // part is contiguous and is broadcast by its owner in the panel's process column in one operation
+    {
+      VcPanelMap& m = st.map;
+      memset(&m, 0, sizeof(m));
+      m.pr = pr; m.nb = nb; m.nt = nt;
+      const int B0 = (st.oe + nb - 1) / nb;            // first distribution block in the buffer (oe is block-aligned)
+      int pos = 0;
+      for (int r = 0; r < pr; ++r) {
+        int bf = B0;
+        while (bf % pr != r) ++bf;
+        m.bfirst[r] = bf;
+        m.chunk_off[r] = pos;
+        int cnt = 0;
+        for (int B = bf; B < nblocks; B += pr) cnt += std::min(nb, nt - B * nb);
+        if (r == 0) { m.main0 = cnt; cnt += nbt; }     // border tiles belong to process row 0
+        if (st.oe < nt && cnt > 0) {
+          BcastOp op;
+          op.off = (int64_t)pos * VC_TILE * Kb;
+          op.count = (int64_t)cnt * VC_TILE * Kb;
+          op.root = r * pc + st.pcp;
+          st.bcasts.push_back(op);
+        }
+        pos += cnt;
+      }
     }
     {
       std::vector<int> tr;
@@ -451,7 +462,7 @@ int vc_dist_n2ll(vc_handle* h, const double* theta, int32_t mu_mode, const doubl
         vc_launch_syrk(g, h->cw.num_sms, h->cw.legacy_syrk, q, &h->launches);
       }
       vc_launch_pack_tiles(base, D->tiles_dev + s.rows.off, s.rows.n,
-                           loc_tile_h(s.ob, nb, D->pc) * VC_TILE, Kb, D->pnl[i & 1], s.oe, q, &h->launches);
+                           loc_tile_h(s.ob, nb, D->pc) * VC_TILE, Kb, D->pnl[i & 1], s.oe, q, &h->launches, &s.map);
     };
     // every distribution block of the panel of step i goes from its owner to all ranks (stream q)
     auto panel_bcast = [&](size_t i, cudaStream_t q) {
@@ -498,6 +509,7 @@ int vc_dist_n2ll(vc_handle* h, const double* theta, int32_t mu_mode, const doubl
       g.K = Kb;
       g.src_a.pnl = D->pnl[i & 1]; g.src_a.ld = VC_TILE; g.src_a.tile_stride = (int64_t)VC_TILE * Kb;
       g.src_a.tile0 = s.oe; g.src_a.col0 = 0;
+      g.src_a.map = s.map;
       g.src_b = g.src_a;
       const bool more = i + 1 < nsteps;
       const bool ws = la && !h->cw.legacy_syrk;
@@ -528,7 +540,7 @@ int vc_dist_n2ll(vc_handle* h, const double* theta, int32_t mu_mode, const doubl
       if (ws && more && D->world > 1 && reserve > 0) {
         const DistStep& nx = D->steps[i + 1];
         const double bytes = 8.0 * (double)(nt + D->nbt - nx.oe) * VC_TILE * (double)(nx.oe - nx.ob) * VC_TILE;
-        const double t_bcast = 300.0 + bytes / 150e3 + 40.0 * (double)nx.bcasts.size();   // us: ~150 GB/s + per-broadcast latency
+        const double t_bcast = 300.0 + bytes / 150e3 + 60.0 * (double)nx.bcasts.size();   // us: ~150 GB/s + per-broadcast latency
         const double t_tile = 17.3 * (Kb / VC_TILE);
         nA = (int)std::min<int64_t>(rest, (int64_t)(safety * t_bcast / t_tile + 1.0) * (nsm - reserve));
       }
