@@ -69,6 +69,7 @@ struct NcclApi {
   void* lib = nullptr;
   int (*GetUniqueId)(ncclUniqueId*) = nullptr;
   int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  int (*CommInitRankConfig)(ncclComm_t*, int, ncclUniqueId, int, void*) = nullptr;   // optional (NCCL >= 2.14)
   int (*CommDestroy)(ncclComm_t) = nullptr;
   int (*Broadcast)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
@@ -96,6 +97,7 @@ struct NcclApi {
     VC_SYM(GroupEnd, "ncclGroupEnd")
     VC_SYM(GetErrorString, "ncclGetErrorString")
 #undef VC_SYM
+    *(void**)(&CommInitRankConfig) = dlsym(lib, "ncclCommInitRankConfig");
     return true;
   }
 };
@@ -119,6 +121,12 @@ extern "C" int vc_nccl_unique_id(char id_out[128]) {
   if (r != 0) return vc_fail(nullptr, VC_ERR_CUDA, std::string("ncclGetUniqueId: ") + g_nccl.GetErrorString(r));
   memcpy(id_out, id.internal, 128);
   return VC_OK;
+}
+
+// SMs the rest update leaves free for NCCL's kernels = CTAs the communicator may use (VC_DIST_RESERVE overrides)
+static int vc_dist_nccl_ctas() {
+  static const int v = getenv("VC_DIST_RESERVE") ? atoi(getenv("VC_DIST_RESERVE")) : 8;
+  return v;
 }
 
 // ---- the distributed state ---------------------------------------------------------------------
@@ -341,7 +349,17 @@ extern "C" int vc_create_dist(vc_handle** out, const vc_config* cfg_in, int64_t 
     build_dist_plan(h, D);
     ncclUniqueId id;
     memcpy(id.internal, nccl_id, 128);
-    VC_NCCL_TRY(g_nccl.CommInitRank(&D->comm, world, id, rank));
+    // The panel broadcasts run BESIDE the trailing update on a handful of SMs left free for them.  NCCL launches one
+    // CTA per channel and a CTA that finds no free SM waits for one -- behind a persistent update kernel that means
+    // until that kernel ends, which serialises broadcast and update.  So cap the communicator's CTAs at the number
+    // of SMs the update leaves free (ncclConfig_t.maxCTAs, v2.17 layout of the struct; older NCCL: plain init).
+    struct { size_t size; unsigned magic, version; int blocking, cgaClusterSize, minCTAs, maxCTAs; const char* netName; } ncfg =
+        {0, 0xcafebeefu, 21701u, INT_MIN, INT_MIN, INT_MIN, INT_MIN, nullptr};
+    ncfg.size = sizeof(ncfg);
+    ncfg.maxCTAs = vc_dist_nccl_ctas();
+    int nrc = -1;
+    if (g_nccl.CommInitRankConfig && ncfg.maxCTAs > 0) nrc = g_nccl.CommInitRankConfig(&D->comm, world, id, rank, &ncfg);
+    if (nrc != 0) VC_NCCL_TRY(g_nccl.CommInitRank(&D->comm, world, id, rank));
   } catch (const VcError& e) {
     if (h) vc_free_handle(h);
     return vc_fail(nullptr, e.code, e.msg);
@@ -411,7 +429,7 @@ int vc_dist_n2ll(vc_handle* h, const double* theta, int32_t mu_mode, const doubl
       VC_CUDA_TRY(cudaEventCreateWithFlags(&D->ev_rows, cudaEventDisableTiming));
     }
     static const int Rd = getenv("VC_DIST_RESERVE_DIAG") ? atoi(getenv("VC_DIST_RESERVE_DIAG")) : 8;
-    static const int Rn = getenv("VC_DIST_RESERVE") ? atoi(getenv("VC_DIST_RESERVE")) : 8;
+    const int Rn = vc_dist_nccl_ctas();
     static const double safety = getenv("VC_DIST_SAFETY") ? atof(getenv("VC_DIST_SAFETY")) : 1.5;
     double* dd_linv = D->dd + (size_t)nb * VC_TILE * ((size_t)nb * VC_TILE);
     // diagonal block of step i on stream q: factor (owner), broadcast L_DD + inverses
