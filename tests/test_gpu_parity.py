@@ -450,6 +450,47 @@ def test_post_matches_prep_par_output_and_eff_dof(n, p, cov):
         assert abs(v - o.n2ll(theta, D, X, W, y, cov, profile=True)) <= TOL_N2LL * abs(v)
 
 
+def test_post_and_predict_at_n8000_against_cusolver_third_path():
+    """prep_par_output / eff_dof (R-pkg/R/utils.R:423-473, R-pkg/R/eff_dof.R:7-21) and predict.SVC_mle
+    (R-pkg/R/predict-SVC_mle.R:80-267) above the sizes the CPU oracle reaches: torch / cuSOLVER forms the explicit
+    inverse of the GPU-built Sigma_y (as the reference does with solve(Sigma)) and evaluates the same formulas."""
+    import torch
+    from varycoef_b200 import SVCObjective
+    n, p, n_new = 8000, 3, 500
+    locs, X, W, y = synth(n, p, 77, 2)
+    theta = theta_for(p)
+    rng = np.random.default_rng(5)
+    newlocs = rng.uniform(0, float(locs.max()), (n_new, 2))
+    newX = np.column_stack([np.ones(n_new), rng.standard_normal((n_new, p - 1))])
+    with SVCObjective(y, X, locs, profileLik=True) as obj:
+        post = obj.post(theta)
+        pred = obj.predict(theta, post["mu_gls"], newlocs, newX, newX, compute_y_var=True)
+        S = torch.from_numpy(obj.Sigma_y(theta)).cuda()
+    Sinv = torch.cholesky_inverse(torch.linalg.cholesky(S))
+    Xd, yd = torch.from_numpy(X).cuda(), torch.from_numpy(y).cuda()
+    SiX = Sinv @ Xd
+    sfe = torch.linalg.inv(Xd.T @ SiX)
+    mu = sfe @ (SiX.T @ yd)
+    tau2 = theta[-1]
+    edof = float(tau2 * torch.trace(sfe @ (SiX.T @ SiX)) + n - tau2 * torch.trace(Sinv))
+    assert np.allclose(post["mu_gls"], mu.cpu().numpy(), rtol=1e-9)
+    assert np.allclose(post["Sigma_FE"], sfe.cpu().numpy(), rtol=1e-8)
+    assert post["edof"] == pytest.approx(edof, rel=1e-9)
+    # EBLUP: eff_k = (cov_k(new, obs) o (newW_k W_k')) alpha restricted to W_k, alpha = Sinv (y - X mu)
+    alpha = Sinv @ (yd - Xd @ mu)
+    nl, ol = torch.from_numpy(newlocs).cuda(), torch.from_numpy(locs).cuda()
+    Dn = torch.cdist(nl, ol)
+    Wd, nW = torch.from_numpy(W).cuda(), torch.from_numpy(newX).cuda()
+    eff = torch.stack([theta[2 * k + 1] * torch.exp(-Dn / theta[2 * k]) @ (Wd[:, k] * alpha) for k in range(p)], 1)
+    assert np.allclose(pred["eff"], eff.cpu().numpy(), rtol=1e-7, atol=1e-9)
+    ypred = (nW * eff).sum(1) + nW @ mu
+    assert np.allclose(pred["y_pred"], ypred.cpu().numpy(), rtol=1e-8)
+    C = sum(theta[2 * k + 1] * torch.exp(-Dn / theta[2 * k]) * torch.outer(nW[:, k], Wd[:, k]) for k in range(p))
+    dg = tau2 + sum(theta[2 * k + 1] * nW[:, k] ** 2 for k in range(p))
+    yvar = dg - ((C @ Sinv) * C).sum(1)
+    assert np.allclose(pred["y_var"], yvar.cpu().numpy(), rtol=1e-7)
+
+
 @pytest.mark.parametrize("n,n_new,p,cov,taper", [(400, 7, 2, "exp", None), (1500, 300, 3, "mat52", None),
                                                  (1200, 150, 2, "exp", 1.0)])
 def test_predict_matches_reference_eblup(n, n_new, p, cov, taper):
