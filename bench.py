@@ -84,9 +84,11 @@ WORKLOADS = {
 TRUE_VAR = [2.0, 1.0, 1.5, 1.0, 0.5]
 TRUE_SCALE = [3.0, 1.0, 2.0, 1.5, 2.5]
 TRUE_MEAN = [1.0, 2.0, 0.5, -1.0, 0.0]
-# DRAM bytes per evaluation from ncu (dram__bytes_read.sum + dram__bytes_write.sum), profiles/r01_traffic_n50k.md
-NCU_TRAFFIC_BYTES = {"c3": 6.163e11}           # potrf + trsm + syrk kernels of one C3 evaluation
+# DRAM bytes per evaluation from ncu (dram__bytes_read.sum + dram__bytes_write.sum), profiles/r02_launches_traffic_n50k.md
+NCU_TRAFFIC_BYTES = {"c3": 6.157e11}           # potrf + trsm + syrk + strip kernels of one C3 evaluation
 NCU_BUILD_TRAFFIC_BYTES = {"c3": 1.002e10}     # k_build_fast + k_border (algorithmic: 1.0e10 written)
+# fp64-pipe instructions per element of k_build_fast<exp, d=2, q=3>, counted in its SASS (profiles/r02_build_alu_floor.md)
+BUILD_FP64_INSTR_PER_ELEMENT = {"c3": 87.5}
 METRIC = "-2logL evals/sec (fp64) at n=50k q=3"
 UNIT = "evals/s"
 
@@ -593,7 +595,7 @@ def run_ours(args):
             "frac": chol_flops / chol_s / 1e12 / peak_tf.value if peak_tf.value > 0 else None,
             "traffic": NCU_TRAFFIC_BYTES.get(args.workload) if at_size else None,
             "traffic_note": "DRAM read + write bytes of all Cholesky kernels of ONE evaluation (per evaluation, like "
-                            "`achieved`), ncu dram__bytes_{read,write}.sum, profiles/r01_traffic_n50k.md: 616 GB in "
+                            "`achieved`), ncu dram__bytes_{read,write}.sum, profiles/r02_launches_traffic_n50k.md: 616 GB in "
                             "1.21 s = 8 % of DRAM peak -- the factorisation is DMMA-bound (pipe 95.7 % active in "
                             "k_syrk_ws, profiles/r01_syrk_ws_n20k.md); the C trapezoid alone accounts for ~400 GB",
             "peak_source": "fp64 DMMA m8n8k4 register-resident probe measured live on this GPU (vc_probe_dmma_peak); "
@@ -603,6 +605,13 @@ def run_ours(args):
                   "peak": hbm_peak, "unit": "GB/s", "frac": build_bytes / build_s / 1e9 / hbm_peak,
                   "traffic": NCU_BUILD_TRAFFIC_BYTES.get(args.workload) if at_size else None, "peak_source": hbm_src,
                   "algorithmic": "4 n (n+1) bytes written (lower triangle) / CUDA-event time of build + border"}
+    ipe = BUILD_FP64_INSTR_PER_ELEMENT.get(args.workload) if at_size else None
+    if ipe and clocks and clocks.get("sm_mhz"):
+        # the kernel is bound by the fp64 pipe, not by HBM: floor = elements x instructions / (SMs x 64 lanes x clock)
+        floor_s = (n * (n + 1) / 2.0) * ipe / (148 * 64 * clocks["sm_mhz"] * 1e6)
+        roof_build["alu_floor"] = {"fp64_instr_per_element": ipe, "floor_ms": floor_s * 1e3, "frac_of_floor": floor_s / build_s,
+                                   "source": "SASS count of the inner loop of k_build_fast<exp,2,3> (profiles/r02_build_alu_floor.md): "
+                                             "DFMA+DMUL+DADD+DSETP per element at 64 fp64 lanes/clk/SM x 148 SMs"}
     h2d = 8 * n * (2 + p + q + 1) + 8 * (2 * q + 1)
     d2h = 8 * 132
     line = {
