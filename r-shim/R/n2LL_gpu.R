@@ -17,6 +17,23 @@ vcb_handle <- function(y, X, locs, W, control) {
         taper_id, if (is.null(control$tapering)) 0 else control$tapering, 0L)
 }
 
+# control$parallel = integer vector of GPU ordinals -> one replica per GPU; batches (optim's stencils, submitted through
+# .Call(C_vcb_n2ll_batch, gpu, thetas, mus)) are spread over them: replaces the optimParallel cluster of SVC_mle.R:164-200
+vcb_handle_multi <- function(y, X, locs, W, control, devices) {
+  cov_id   <- match(control$cov.name, c("exp", "mat32", "mat52", "sph", "wend1", "wend2")) - 1L
+  dist_id  <- match(control$dist$method, c("euclidean", "maximum", "manhattan", "minkowski")) - 1L
+  taper_id <- if (is.null(control$tapering)) 0L else switch(control$cov.name, exp = 1L, mat32 = 1L, mat52 = 2L)
+  .Call(C_vcb_create_multi, as.matrix(locs), as.matrix(X), as.matrix(W), as.numeric(y), cov_id, dist_id,
+        if (is.null(control$dist$p)) 2 else control$dist$p, taper_id,
+        if (is.null(control$tapering)) 0 else control$tapering, as.integer(devices))
+}
+
+# med_dist <- median(as.numeric(d)) (SVC_mle.R:39-45) without the n x n matrix
+med_dist_gpu <- function(locs, control)
+  .Call(C_vcb_median_dist, as.matrix(locs),
+        match(control$dist$method, c("euclidean", "maximum", "manhattan", "minkowski")) - 1L,
+        if (is.null(control$dist$p)) 2 else control$dist$p, 0L)
+
 n2LL <- function(x, cov_func, outer.W, y, X, W, mean.est = NULL, taper = NULL,
                  pc.dens = NULL, Rstruct = NULL, profile = TRUE, gpu = NULL) {
   q <- dim(W)[2]; p <- dim(X)[2]
@@ -28,7 +45,7 @@ n2LL <- function(x, cov_func, outer.W, y, X, W, mean.est = NULL, taper = NULL,
 #   - drop `d <- own_dist(...)`, `outer.W <- lapply(...)`, `taper`, `Rstruct`   (lines 33-36, 63-81)
 #   - gpu <- vcb_handle(y, X, locs, W, control)
 #   - pass `gpu = gpu` in the optim()/optimParallel() argument list and in `args` of extract_fun
-#   - med_dist: median of the pairwise distances still needed for default bounds (host, once)
+#   - med_dist <- med_dist_gpu(locs, control)   (dense branch; the tapered branch is the constant 1, SVC_mle.R:44)
 
 # After the optimisation (R-pkg/R/SVC_mle.R:205-296) the O(n^3) post-processing also comes from the resident factor:
 #   post <- .Call(C_vcb_post, gpu, cov.par, p, TRUE)      # list(mu_GLS, Sigma_FE = (X' S^-1 X)^-1, edof)

@@ -7,6 +7,7 @@ typedef struct SEXPREC* SEXP;
 typedef int Rboolean;
 #define TRUE 1
 #define FALSE 0
+#define INTSXP 13
 #define REALSXP 14
 #define VECSXP 19
 extern SEXP R_NilValue;
@@ -14,6 +15,7 @@ extern double R_NaReal;
 #define NA_REAL R_NaReal
 void Rf_error(const char*, ...);
 double* REAL(SEXP);
+int* INTEGER(SEXP);
 int Rf_asInteger(SEXP);
 double Rf_asReal(SEXP);
 int Rf_asLogical(SEXP);

@@ -56,6 +56,45 @@ SEXP vcb_create(SEXP locs, SEXP X, SEXP W, SEXP y, SEXP cov_id, SEXP dist_id, SE
   return ext;
 }
 
+/* .Call(C_vcb_create_multi, locs, X, W, y, cov_id, dist_id, mink_p, taper_id, taper_range, devices): one replica per GPU;
+ * vcb_n2ll_batch then spreads a batch over them -- what control$parallel / optimParallel did with PSOCK workers
+ * (R-pkg/R/SVC_mle.R:164-200) */
+SEXP vcb_create_multi(SEXP locs, SEXP X, SEXP W, SEXP y, SEXP cov_id, SEXP dist_id, SEXP mink_p,
+                      SEXP taper_id, SEXP taper_range, SEXP devices) {
+  vc_config cfg;
+  vc_config_default(&cfg);
+  cfg.cov_id = Rf_asInteger(cov_id);
+  cfg.dist_method = Rf_asInteger(dist_id);
+  cfg.minkowski_p = Rf_asReal(mink_p);
+  cfg.taper_id = Rf_asInteger(taper_id);
+  cfg.taper_range = Rf_asReal(taper_range);
+  locs = PROTECT(Rf_coerceVector(locs, REALSXP));
+  X = PROTECT(Rf_coerceVector(X, REALSXP));
+  W = PROTECT(Rf_coerceVector(W, REALSXP));
+  y = PROTECT(Rf_coerceVector(y, REALSXP));
+  devices = PROTECT(Rf_coerceVector(devices, INTSXP));
+  vc_handle* h = NULL;
+  int rc = vc_create_multi(&h, &cfg, (int64_t) Rf_nrows(X), Rf_ncols(locs), Rf_ncols(X), Rf_ncols(W),
+                           REAL(locs), REAL(X), REAL(W), REAL(y), INTEGER(devices), Rf_length(devices));
+  if (rc != VC_OK) Rf_error("varycoef_b200 (%d): %s", rc, vc_last_error(NULL));
+  SEXP ext = PROTECT(R_MakeExternalPtr(h, R_NilValue, R_NilValue));
+  R_RegisterCFinalizerEx(ext, vcb_finalizer, TRUE);
+  UNPROTECT(6);
+  return ext;
+}
+
+/* .Call(C_vcb_median_dist, locs, dist_id, mink_p, device) -> med_dist: median(as.numeric(d)) of MLE_computation
+ * (R-pkg/R/SVC_mle.R:39-45, dense branch) without the n x n distance matrix */
+SEXP vcb_median_dist(SEXP locs, SEXP dist_id, SEXP mink_p, SEXP device) {
+  locs = PROTECT(Rf_coerceVector(locs, REALSXP));
+  double med = NA_REAL;
+  int rc = vc_median_dist(Rf_asInteger(device), (int64_t) Rf_nrows(locs), Rf_ncols(locs), REAL(locs),
+                          Rf_asInteger(dist_id), Rf_asReal(mink_p), &med, NULL);
+  UNPROTECT(1);
+  if (rc != VC_OK) Rf_error("varycoef_b200 (%d): %s", rc, vc_last_error(NULL));
+  return Rf_ScalarReal(med);
+}
+
 /* .Call(C_vcb_n2ll, handle, theta, mu or NULL, p) -> numeric(1) with attributes mu (length p), logdet, quad */
 SEXP vcb_n2ll(SEXP ext, SEXP theta, SEXP mu, SEXP p_) {
   vc_handle* h = vcb_get(ext);
@@ -152,6 +191,8 @@ SEXP vcb_gls_chol(SEXP R, SEXP X, SEXP y, SEXP device) {
 
 static const R_CallMethodDef vcb_calls[] = {
   {"C_vcb_create", (DL_FUNC) &vcb_create, 10},
+  {"C_vcb_create_multi", (DL_FUNC) &vcb_create_multi, 10},
+  {"C_vcb_median_dist", (DL_FUNC) &vcb_median_dist, 4},
   {"C_vcb_n2ll", (DL_FUNC) &vcb_n2ll, 4},
   {"C_vcb_n2ll_batch", (DL_FUNC) &vcb_n2ll_batch, 3},
   {"C_vcb_post", (DL_FUNC) &vcb_post, 4},

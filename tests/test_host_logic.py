@@ -232,7 +232,7 @@ def test_r_shim_type_checks_against_the_header():
                          capture_output=True, text=True)
     assert out.returncode == 0, out.stderr
     src = open(os.path.join(ROOT, "r-shim", "src", "varycoef_b200_r.c")).read()
-    for fn in ("vc_create", "vc_n2ll", "vc_n2ll_batch", "vc_post", "vc_predict", "vc_get_whitened", "vc_gls_chol",
+    for fn in ("vc_create", "vc_create_multi", "vc_median_dist", "vc_n2ll", "vc_n2ll_batch", "vc_post", "vc_predict", "vc_get_whitened", "vc_gls_chol",
                "vc_destroy", "vc_last_error", "vc_last_info"):
         assert fn + "(" in src, fn
 
@@ -252,3 +252,61 @@ def test_plain_c_client_links_and_validates_arguments(tmp_path):
     assert run.returncode == 0, (run.returncode, run.stdout, run.stderr)
     assert run.stdout.startswith("abi ")
     assert ("no gpu:" in run.stdout) or ("n2ll " in run.stdout)
+
+
+def test_owner_major_panel_map_is_a_bijection_with_contiguous_owner_ranges():
+    """Sharded path: the gathered panel buffer holds the row tiles >= oe in OWNER-major order (VcPanelMap,
+    csrc/vc_common.cuh) so that every process row's part is ONE contiguous range = one NCCL broadcast.  The device
+    function vc_panel_pos is compiled for the host here and checked for every step of a few grids: positions are a
+    bijection onto 0 .. count-1, every owner's tiles are contiguous and in tile order, border tiles follow process
+    row 0's main tiles."""
+    src = r"""
+#include <stdio.h>
+#include <string.h>
+#include "vc_common.cuh"
+int main(int argc, char** argv) {
+  int nt, nb, pr, nbt, oe;
+  while (scanf("%d %d %d %d %d", &nt, &nb, &pr, &nbt, &oe) == 5) {
+    VcPanelMap m; memset(&m, 0, sizeof(m));
+    m.pr = pr; m.nb = nb; m.nt = nt;
+    const int nblocks = (nt + nb - 1) / nb, B0 = (oe + nb - 1) / nb;
+    int pos = 0;
+    for (int r = 0; r < pr; ++r) {                        // as build_dist_plan (csrc/vc_dist.cu) fills it
+      int bf = B0; while (bf % pr != r) ++bf;
+      m.bfirst[r] = bf; m.chunk_off[r] = pos;
+      int cnt = 0;
+      for (int B = bf; B < nblocks; B += pr) cnt += (nt - B * nb < nb ? nt - B * nb : nb);
+      if (r == 0) { m.main0 = cnt; cnt += nbt; }
+      pos += cnt;
+    }
+    for (int I = oe; I < nt + nbt; ++I) printf("%d ", vc_panel_pos(m, I, oe));
+    printf("\n");
+  }
+  return 0;
+}
+"""
+    import tempfile
+    cases = []
+    for nt, nb, pr, nbt in [(40, 4, 2, 1), (41, 4, 4, 1), (37, 8, 4, 2), (16, 2, 1, 1), (1172, 8, 4, 1)]:
+        for oe in range(nb, nt, nb * (1 if nt < 100 else 37)):
+            cases.append((nt, nb, pr, nbt, oe))
+    with tempfile.TemporaryDirectory() as td:
+        cpp = os.path.join(td, "t.cpp")
+        open(cpp, "w").write(src)
+        exe = os.path.join(td, "t")
+        subprocess.check_call(["g++", "-O1", "-x", "c++", "-I", os.path.join(ROOT, "varycoef_b200", "csrc"),
+                               "-I", "/usr/local/cuda/include", cpp, "-o", exe])
+        out = subprocess.run([exe], input="".join("%d %d %d %d %d\n" % c for c in cases), capture_output=True, text=True,
+                             check=True).stdout.strip().split("\n")
+    assert len(out) == len(cases)
+    for (nt, nb, pr, nbt, oe), line in zip(cases, out):
+        pos = [int(v) for v in line.split()]
+        tiles = list(range(oe, nt + nbt))
+        assert sorted(pos) == list(range(len(tiles))), (nt, nb, pr, oe)
+        owner = [((I // nb) % pr) if I < nt else 0 for I in tiles]
+        for r in range(pr):
+            mine = [(q, I) for q, I, o in zip(pos, tiles, owner) if o == r]
+            if mine:
+                qs = [q for q, _ in mine]
+                assert qs == list(range(min(qs), min(qs) + len(qs))), (nt, nb, pr, oe, r)     # contiguous, in tile order
+        # plain order when pr == 0 is covered by the device tests of the 1 x 1 grid
