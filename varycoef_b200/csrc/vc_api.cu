@@ -492,7 +492,6 @@ extern "C" int vc_n2ll_batch(vc_handle* h, int32_t m, const double* thetas, int3
       VcMatrix M = h->M;
       M.nbatch = gsz;
       M.nbt = 1;
-      M.border_rows = h->p + 1;            // [X y]^T
       const bool timed = last_group;
       if (timed) VC_CUDA_TRY(cudaEventRecord(h->ev[0], st));
       if (!cached) {

@@ -410,36 +410,6 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_syrk_ws(GemmArgs p) {
       const int I = packed & 0xffff, J = packed >> 16;
       int64_t ldc;
       double* Ct = c_tile_ptr(p, e, I, J, ldc);
-      if (p.border_strip && I >= p.nt) {
-        // Border tile whose right-hand sides fill at most 32 of its 128 rows ([X y]^T: p + 1 rows): only that
-        // 32-row strip is updated, a quarter of the DMMA work; the eight warps share it as 32 x 16 slabs.  Same
-        // k order per element as the full tile, so the result is bit-identical; rows 32..127 stay exactly zero.
-        double accs[4][2][2];
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-          for (int j = 0; j < 2; ++j) accs[i][j][0] = accs[i][j][1] = 0.0;
-        for (int kt = 0; kt < nk; ++kt, ++it) {
-          const unsigned slot = it % WS_STAGES;
-          mbar_wait(full + slot, (it / WS_STAGES) & 1);
-          __syncwarp();
-          const double* sa = smem + slot * STAGE_DOUBLES;
-          warp_stage_strip(sa + g, sa + KC * SLD + warp * 16 + g, tig, accs);
-          asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-          __syncwarp();
-          if (lane == 0) mbar_arrive(empty + slot);
-        }
-        double* cs = Ct + g + (int64_t)(warp * 16 + 2 * tig) * ldc;
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            double* c = cs + i * 8 + (int64_t)(j * 8) * ldc;
-            red_add_f64(c, -accs[i][j][0]);
-            red_add_f64(c + ldc, -accs[i][j][1]);
-          }
-        continue;
-      }
       double* cbase = Ct + (wm * 64 + g) + (int64_t)(wn * 32 + 2 * tig) * ldc;
       double acc[8][4][2];
 #pragma unroll
@@ -1462,7 +1432,6 @@ static GemmArgs base_args(const VcMatrix& M) {
   g.a = M.a; g.cb = M.cb; g.blk = M.blk; g.pr = 1; g.pc = 1; g.b = M.b; g.ldb = M.ldb; g.nt = M.nt;
   g.nbatch = std::max(M.nbatch, 1); g.a_es = M.a_es; g.b_es = M.b_es;
   g.linv_es = (int64_t)M.nt * TILE * TILE;
-  g.border_strip = (M.border_rows > 0 && M.border_rows <= STRIP) ? 1 : 0;
   return g;
 }
 

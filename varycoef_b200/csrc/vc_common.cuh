@@ -99,7 +99,6 @@ struct VcMatrix {        // padded Sigma / factor in HBM (lower block-column tra
   double* b;             // border: (128 * nbt) x n_pad column-major; rows = right-hand sides B^T,
   int64_t ldb;           //         turned into (L^-1 B)^T by the factorisation / solve sweep
   int nbt;               // border row tiles in use
-  int border_rows;       // rows of a border tile that carry right-hand sides (0 = all 128); <= 32: strip updates
 };
 
 // vc_build.cu
@@ -168,7 +167,6 @@ struct VcGemmArgs {       // by-value argument block of k_trsm_panel / k_syrk_ws
   int ntiles;
   VcOpSrc src_a, src_b;   // operand sources of the update kernels
   int i_skip;             // TRSM without tile list: main row tiles start at jt + 1 + i_skip
-  int border_strip;       // update kernels: border tiles (I >= nt) carry <= 32 rows, update only that strip
   int lin_first, lin_stop;  // update kernels: first linear (slot, tile) index of k_strip / stop index of k_syrk_ws (0 = all)
 };
 struct VcUpdateCall {     // one trailing / inner update of the factorisation plan

@@ -408,7 +408,6 @@ int vc_dist_n2ll(vc_handle* h, const double* theta, int32_t mu_mode, const doubl
     base.a = h->M.a; base.cb = h->M.cb; base.b = h->M.b; base.ldb = h->M.ldb; base.nt = nt;
     base.blk = nb; base.pr = D->pr; base.pc = D->pc;
     base.nbatch = 1;
-    base.border_strip = (p + 1 <= 32) ? 1 : 0;          // [X y]^T fills p + 1 rows of the border tile
     // Schedule of one outer block (lookahead; sm = main stream, sp = high-priority panel stream):
     //   sm: colD(s)  | colR(s) on num_sms - Rd ............ | rows(s+1) at FULL width | rest(s): part A on num_sms - Rn, part B on all
     //   sp:          '-> diag(s+1): L_DD chain, NCCL bcast -^             '-> NCCL panel broadcast(s+1), beside part A
