@@ -201,6 +201,12 @@ VC_API int vc_create_dist(vc_handle** h, const vc_config* cfg, int64_t n, int32_
  * n^2 8 (1/pr + 1/pc) / 2 a row / column-communicator scheme would need */
 VC_API int vc_dist_traffic(vc_handle* h, double* rx_bytes, double* rowcol_bound_bytes);
 
+/* host-only plan of a batch of m evaluations under S evaluation slots (no GPU needed; unit tests): evaluations that
+ * repeat theta share a slot, the last valid evaluation lands in slot 0 of the last group.  valid may be NULL.
+ * Returns the number of distinct thetas; group_of / slot_of / rec_of (m each) are -1 for invalid evaluations. */
+VC_API int vc_plan_batch(int32_t m, int32_t nth, const double* thetas, const int32_t* valid, int32_t S,
+                         int32_t* group_of, int32_t* slot_of, int32_t* rec_of);
+
 /* host-only block-cyclic map (no GPU needed): owner rank and local tile index of 512-block (bi, bj) */
 VC_API int vc_bc_owner(int32_t bi, int32_t bj, int32_t pr, int32_t pc);
 VC_API int vc_bc_local(int32_t b, int32_t nprocs_dim);

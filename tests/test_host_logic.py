@@ -310,3 +310,44 @@ int main(int argc, char** argv) {
                 qs = [q for q, _ in mine]
                 assert qs == list(range(min(qs), min(qs) + len(qs))), (nt, nb, pr, oe, r)     # contiguous, in tile order
         # plain order when pr == 0 is covered by the device tests of the 1 x 1 grid
+
+
+def test_batch_plan_shares_slots_between_repeated_thetas_and_puts_the_last_evaluation_in_slot_0():
+    """vc_plan_batch (host part of vc_n2ll_batch): every distinct theta gets exactly one slot per call, evaluations
+    that repeat it share that slot (one factorisation, several finalize jobs), groups hold at most S slots, the
+    theta of the LAST valid evaluation sits in slot 0 of the LAST group (what vc_get_chol / vc_post refer to),
+    result records are dense and in evaluation order within a group, invalid evaluations get nothing."""
+    import ctypes as C
+    from varycoef_b200 import _lib
+    L = _lib.lib()
+    rng = np.random.default_rng(0)
+    for m, nd, S in [(1, 1, 1), (9, 4, 32), (21, 15, 4), (100, 41, 32), (50, 50, 7), (13, 1, 3)]:
+        base = rng.uniform(0.5, 2.0, (nd, 7))
+        pick = rng.integers(0, nd, m)
+        pick[:nd] = np.arange(nd)[:m]                      # every distinct theta occurs (when m >= nd)
+        thetas = np.ascontiguousarray(base[pick])
+        valid = np.ones(m, dtype=np.int32)
+        if m > 5:
+            valid[rng.integers(0, m, 2)] = 0
+        g, s, r = (np.empty(m, dtype=np.int32) for _ in range(3))
+        ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int32))
+        nu = L.vc_plan_batch(m, 7, _lib.ptr(thetas), ip(valid), S, ip(g), ip(s), ip(r))
+        ok = valid == 1
+        assert nu == len({tuple(t) for t in thetas[ok]})
+        assert np.all(g[~ok] == -1) and np.all(s[~ok] == -1) and np.all(r[~ok] == -1)
+        # same theta <-> same (group, slot)
+        key = {}
+        for e in np.nonzero(ok)[0]:
+            key.setdefault(tuple(thetas[e]), set()).add((int(g[e]), int(s[e])))
+        assert all(len(v) == 1 for v in key.values())
+        assert len({next(iter(v)) for v in key.values()}) == nu           # distinct thetas never share a slot
+        ngroups = int(g[ok].max()) + 1
+        assert ngroups == -(-nu // S)
+        for gi in range(ngroups):
+            slots = sorted({int(x) for x in s[ok & (g == gi)]})
+            assert slots == list(range(len(slots))) and len(slots) <= S   # dense slots 0 .. gsz-1
+        last = int(np.nonzero(ok)[0][-1])
+        assert g[last] == ngroups - 1 and s[last] == 0
+        # records: dense, grouped by group, in evaluation order inside a group
+        order = sorted(np.nonzero(ok)[0], key=lambda e: (g[e], e))
+        assert [int(r[e]) for e in order] == list(range(len(order)))

@@ -374,6 +374,66 @@ int vc_make_theta(const vc_handle* h, const double* theta, VcTheta* t) {
   return VC_OK;
 }
 
+// ---- host-side plan of a batch (no CUDA: unit-tested on the CPU through vc_plan_batch) ----------------------
+// Distinct thetas (optim's probes of the mean parameters in the non-profile objective repeat theta: they share
+// one factorisation and differ only in the O(n p) finalize job), processed in groups of at most S slots; the theta
+// of the last valid evaluation goes LAST so that it lands in slot 0 of the last group (vc_get_chol /
+// vc_get_whitened / vc_post refer to slot 0).
+struct VcBatchPlan {
+  std::vector<int> uniq;      // first evaluation of every distinct theta
+  std::vector<int> uniq_of;   // evaluation -> distinct index (-1: invalid theta)
+  std::vector<int> order;     // distinct thetas in processing order
+  int last_valid = -1;
+};
+static void plan_batch(int m, int nth, const double* thetas, const std::vector<int>& status, VcBatchPlan& pl) {
+  pl.uniq.clear(); pl.order.clear();
+  pl.uniq_of.assign(m, -1);
+  pl.last_valid = -1;
+  for (int e = 0; e < m; ++e) {
+    if (status[e] != VC_OK) continue;
+    int u = -1;
+    for (size_t k = 0; k < pl.uniq.size() && u < 0; ++k)
+      if (memcmp(thetas + (size_t)pl.uniq[k] * nth, thetas + (size_t)e * nth, nth * sizeof(double)) == 0) u = (int)k;
+    if (u < 0) { u = (int)pl.uniq.size(); pl.uniq.push_back(e); }
+    pl.uniq_of[e] = u;
+    pl.last_valid = e;
+  }
+  const int nu = (int)pl.uniq.size();
+  const int u_last = pl.last_valid >= 0 ? pl.uniq_of[pl.last_valid] : -1;
+  for (int u = 0; u < nu; ++u) if (u != u_last) pl.order.push_back(u);
+  if (u_last >= 0) pl.order.push_back(u_last);
+}
+// slot i of the group order[g0 .. g0 + gsz) holds distinct theta order[g0 + gsz - 1 - i]: its last theta sits in slot 0
+static void group_slots(const VcBatchPlan& pl, int g0, int gsz, std::vector<int>& slot_of_u) {
+  slot_of_u.assign(pl.uniq.size(), -1);
+  for (int i = 0; i < gsz; ++i) slot_of_u[pl.order[g0 + gsz - 1 - i]] = i;
+}
+// Test hook (host only): for every evaluation its group, slot and result record under S slots; -1 for invalid ones.
+extern "C" int vc_plan_batch(int32_t m, int32_t nth, const double* thetas, const int32_t* valid, int32_t S,
+                             int32_t* group_of, int32_t* slot_of, int32_t* rec_of) {
+  if (m < 1 || nth < 1 || !thetas || S < 1 || !group_of || !slot_of || !rec_of) return -1;
+  std::vector<int> status(m, VC_OK);
+  for (int e = 0; e < m; ++e) if (valid && !valid[e]) status[e] = VC_ERR_INVALID;
+  VcBatchPlan pl;
+  plan_batch(m, nth, thetas, status, pl);
+  const int nu = (int)pl.uniq.size();
+  for (int e = 0; e < m; ++e) group_of[e] = slot_of[e] = rec_of[e] = -1;
+  int rec_base = 0, g = 0;
+  for (int g0 = 0; g0 < nu; g0 += S, ++g) {
+    const int gsz = std::min((int)S, nu - g0);
+    std::vector<int> slot_of_u;
+    group_slots(pl, g0, gsz, slot_of_u);
+    int njobs = 0;
+    for (int e = 0; e < m; ++e) {
+      if (status[e] != VC_OK || slot_of_u[pl.uniq_of[e]] < 0) continue;
+      group_of[e] = g; slot_of[e] = slot_of_u[pl.uniq_of[e]]; rec_of[e] = rec_base + njobs;
+      ++njobs;
+    }
+    rec_base += njobs;
+  }
+  return nu;
+}
+
 // how many evaluation slots a batch may use: one evaluation fills the GPU from n ~ 25k on
 static int slot_cap(const vc_handle* h) {
   if (h->dist) return 1;
@@ -432,21 +492,15 @@ extern "C" int vc_n2ll_batch(vc_handle* h, int32_t m, const double* thetas, int3
     VC_CUDA_TRY(cudaSetDevice(h->device));
     ensure_result_slots(h, m);
     std::vector<int> status(m, VC_OK);
-    // ---- jobs with a valid theta; distinct thetas (optim's probes of the mean parameters in the non-profile
-    // objective repeat theta: they share one factorisation and differ only in the O(n p) finalize) ----
-    std::vector<int> uniq_of(m, -1);            // evaluation -> index into `uniq`
-    std::vector<int> uniq;                      // first evaluation of every distinct theta
     for (int e = 0; e < m; ++e) {
       VcTheta th;
-      if (vc_make_theta(h, thetas + (size_t)e * nth, &th) != VC_OK) { status[e] = VC_ERR_INVALID; continue; }
-      int u = -1;
-      for (size_t k = 0; k < uniq.size() && u < 0; ++k)
-        if (memcmp(thetas + (size_t)uniq[k] * nth, thetas + (size_t)e * nth, nth * sizeof(double)) == 0) u = (int)k;
-      if (u < 0) { u = (int)uniq.size(); uniq.push_back(e); }
-      uniq_of[e] = u;
+      if (vc_make_theta(h, thetas + (size_t)e * nth, &th) != VC_OK) status[e] = VC_ERR_INVALID;
     }
-    int last_valid = -1;
-    for (int e = m - 1; e >= 0 && last_valid < 0; --e) if (status[e] == VC_OK) last_valid = e;
+    VcBatchPlan bp;
+    plan_batch(m, nth, thetas, status, bp);
+    const std::vector<int>& uniq_of = bp.uniq_of;
+    const std::vector<int>& uniq = bp.uniq;
+    const int last_valid = bp.last_valid;
     const int nu = (int)uniq.size();
     // the resident factor of slot 0 (a repeated theta, vc_post after a fit) is reused when the whole call is about it
     const bool cached = nu == 1 && h->factor_theta.size() == (size_t)nth &&
@@ -455,10 +509,7 @@ extern "C" int vc_n2ll_batch(vc_handle* h, int32_t m, const double* thetas, int3
     if (nu > 1) S = ensure_slots(h, std::min(nu, slot_cap(h)));
     // order of the distinct thetas: the theta of the last valid evaluation goes last, so that it lands in slot 0
     // of the last group (vc_get_chol / vc_get_whitened / vc_post refer to slot 0)
-    std::vector<int> order;
-    const int u_last = last_valid >= 0 ? uniq_of[last_valid] : -1;
-    for (int u = 0; u < nu; ++u) if (u != u_last) order.push_back(u);
-    if (u_last >= 0) order.push_back(u_last);
+    const std::vector<int>& order = bp.order;
     std::vector<int> rec_of(m, -1);             // evaluation -> result record
     int rec_base = 0;
     cudaStream_t st = h->st_main;
@@ -466,12 +517,10 @@ extern "C" int vc_n2ll_batch(vc_handle* h, int32_t m, const double* thetas, int3
       const int gsz = std::min(S, nu - g0);
       const bool last_group = g0 + gsz >= nu;
       // slot i of this group holds distinct theta order[g0 + gsz - 1 - i]: the group's last theta sits in slot 0
-      std::vector<int> slot_of_u(nu, -1);
-      for (int i = 0; i < gsz; ++i) {
-        const int u = order[g0 + gsz - 1 - i];
-        slot_of_u[u] = i;
-        vc_make_theta(h, thetas + (size_t)uniq[u] * nth, &h->thetas_host[g0 + i]);
-      }
+      std::vector<int> slot_of_u;
+      group_slots(bp, g0, gsz, slot_of_u);
+      for (int i = 0; i < gsz; ++i)
+        vc_make_theta(h, thetas + (size_t)uniq[order[g0 + gsz - 1 - i]] * nth, &h->thetas_host[g0 + i]);
       // jobs of this group, in evaluation order
       int njobs = 0;
       for (int e = 0; e < m; ++e) {
