@@ -38,6 +38,17 @@ int main(void) {
   printf("n2ll %.12f mu %.9f %.9f logdet %.9f quad %.9f\n", val, mu[0], mu[1], logdet, quad);
   const double bad[2 * Q + 1] = {-1.0, 0.8, 1.0, 0.4, 0.3};
   if (vc_n2ll(h, bad, VC_MU_GLS, NULL, &val, mu, NULL, NULL) != VC_ERR_INVALID) { vc_destroy(h); return 17; }
+  /* a batch: three thetas, the first and the last equal (they share one factorisation), bit-identical to vc_n2ll */
+  const double th3[3 * (2 * Q + 1)] = {1.5, 0.8, 1.0, 0.4, 0.3, 1.6, 0.8, 1.0, 0.4, 0.3, 1.5, 0.8, 1.0, 0.4, 0.3};
+  double v3[3];
+  int32_t st3[3];
+  if (vc_n2ll_batch(h, 3, th3, VC_MU_GLS, NULL, v3, NULL, st3) != VC_OK) { vc_destroy(h); return 18; }
+  if (v3[0] != v3[2] || st3[1] != VC_OK) { vc_destroy(h); return 19; }
+  if (vc_n2ll(h, theta, VC_MU_GLS, NULL, &val, mu, NULL, NULL) != VC_OK || val != v3[0]) { vc_destroy(h); return 20; }
+  /* med_dist of MLE_computation: 40 equispaced points at 0.25 -> median of all 1600 |i - j| / 4 */
+  double med = -1.0;
+  if (vc_median_dist(0, N, D, locs, VC_DIST_EUCLIDEAN, 2.0, &med, NULL) != VC_OK) { vc_destroy(h); return 21; }
+  printf("batch %.12f %.12f median_dist %.6f devices %d\n", v3[0], v3[1], med, vc_device_count(h));
   vc_destroy(h);
   return 0;
 }

@@ -725,6 +725,33 @@ def test_median_dist_on_gpu_is_exactly_the_host_median():
     assert median_dist(locs) == o.median_dist(locs)
 
 
+def test_plain_c_client_runs_its_gpu_branch(tmp_path):
+    """The drop-in boundary is a C ABI: a C99 program with no Python in sight (tests/c/abi_client.c) creates a handle,
+    evaluates -2logL, a batch and med_dist on the GPU; its numbers must equal the oracle's."""
+    import os
+    import subprocess
+    from varycoef_b200 import _build
+    o = _oracle()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib = _build.build()
+    exe = str(tmp_path / "abi_client")
+    subprocess.check_call(["gcc", "-std=c99", "-I" + os.path.join(root, "include"), os.path.join(root, "tests", "c", "abi_client.c"),
+                           "-o", exe, "-L" + os.path.dirname(lib), "-lvarycoef_b200", "-lm", "-Wl,-rpath," + os.path.dirname(lib)])
+    run = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert run.returncode == 0, (run.returncode, run.stdout, run.stderr)
+    line = [ln for ln in run.stdout.splitlines() if ln.startswith("n2ll ")]
+    assert line, run.stdout
+    val = float(line[0].split()[1])
+    i = np.arange(40)
+    locs = 0.25 * i
+    X = np.column_stack([np.ones(40), np.sin(0.7 * i)])
+    y = 1.0 + 2.0 * X[:, 1] + 0.3 * np.cos(1.3 * i)
+    ref = o.n2ll(np.array([1.5, 0.8, 1.0, 0.4, 0.3]), o.own_dist(locs), X, X, y, "exp", profile=True)
+    assert abs(val - ref) <= TOL_N2LL * abs(ref)
+    med = float([ln for ln in run.stdout.splitlines() if ln.startswith("batch ")][0].split()[4])
+    assert abs(med - float(np.median(o.own_dist(locs)))) < 1e-6
+
+
 def test_fallback_kernels_agree_with_default_path():
     """VC_FLAG_LEGACY_POTRF (unblocked diagonal-tile kernel) and VC_FLAG_NO_LOOKAHEAD give the same
     likelihood as the default kernels up to rounding."""
