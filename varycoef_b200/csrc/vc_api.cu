@@ -278,6 +278,8 @@ static int multi_batch(vc_handle* h, int32_t m, const double* thetas, int32_t mu
                        double* out_n2ll, double* out_mu, int32_t* out_status) {
   const int nth = 2 * h->q + 1, p = h->p;
   const int G = (int)h->kids.size();
+  h->last_info = 0;
+  h->err.clear();
   // distinct thetas, in order of first appearance; all evaluations of one theta go to the same device
   std::vector<int> uniq, uniq_of(m);
   for (int e = 0; e < m; ++e) {
@@ -295,6 +297,7 @@ static int multi_batch(vc_handle* h, int32_t m, const double* thetas, int32_t mu
   std::vector<std::vector<double>> th(G), mu(G), val(G), muo(G);
   std::vector<std::vector<int32_t>> st(G);
   std::vector<std::thread> workers;
+  bool spawn_failed = false;
   for (int g = 0; g < G; ++g) {
     const int mg = (int)evals[g].size();
     if (mg == 0) continue;
@@ -304,12 +307,19 @@ static int multi_batch(vc_handle* h, int32_t m, const double* thetas, int32_t mu
       memcpy(&th[g][(size_t)i * nth], thetas + (size_t)evals[g][i] * nth, nth * sizeof(double));
       if (mus_in) memcpy(&mu[g][(size_t)i * p], mus_in + (size_t)evals[g][i] * p, p * sizeof(double));
     }
-    workers.emplace_back([&, g, mg]() {
+    auto work = [&, g, mg]() {
       rcs[g] = vc_n2ll_batch(h->kids[g], mg, th[g].data(), mu_mode, mus_in ? mu[g].data() : nullptr, val[g].data(),
                              muo[g].data(), st[g].data());
-    });
+    };
+    try {
+      workers.emplace_back(work);            // one host thread per device: vc_n2ll_batch blocks until its results are back
+    } catch (const std::exception&) {        // no thread to be had: run this device's share on the calling thread
+      spawn_failed = true;
+      work();
+    }
   }
   for (auto& w : workers) w.join();
+  (void)spawn_failed;
   int first = VC_OK;
   for (int g = 0; g < G; ++g) {
     const int mg = (int)evals[g].size();
@@ -615,7 +625,8 @@ extern "C" int vc_n2ll(vc_handle* h, const double* theta, int32_t mu_mode, const
   if (!h->kids.empty()) {            // a lone evaluation runs on the child that holds the last factor (cache hits)
     vc_handle* k = vc_target(h);
     const int rc = vc_n2ll(k, theta, mu_mode, mu_in, n2ll, mu_out, logdet, quad);
-    if (rc != VC_OK) { h->err = k->err; h->last_info = k->last_info; }
+    h->last_info = k->last_info;
+    h->err = rc != VC_OK ? k->err : std::string();
     return rc;
   }
   if (h->dist) return vc_dist_n2ll(h, theta, mu_mode, mu_in, n2ll, mu_out, logdet, quad);
