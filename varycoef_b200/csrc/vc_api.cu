@@ -111,6 +111,7 @@ static void ensure_result_slots(vc_handle* h, int m) {
 
 // per-SLOT buffers: matrix, border, diagonal-tile inverses, log-det partials, info, theta staging
 static void alloc_slot_buffers(vc_handle* h, int S) {
+  vc_chol_free_graphs(h->cw);            // captured graphs hold the old addresses
   cudaFree(h->M.a); cudaFree(h->M.b); cudaFree(h->cw.linv); cudaFree(h->cw.logdet_part); cudaFree(h->cw.info);
   cudaFree(h->thetas_dev);
   h->M.a = h->M.b = h->cw.linv = h->cw.logdet_part = nullptr;

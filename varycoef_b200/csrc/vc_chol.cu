@@ -1303,7 +1303,9 @@ void vc_chol_invert_diag_tiles(const VcMatrix& M, VcCholWork& w, int64_t* launch
   }
 }
 
+void vc_chol_free_graphs(VcCholWork& w);
 void vc_chol_free_plans(VcCholWork& w) {
+  vc_chol_free_graphs(w);
   if (w.plan_factor.tiles_dev) cudaFree(w.plan_factor.tiles_dev);
   if (w.plan_solve.tiles_dev) cudaFree(w.plan_solve.tiles_dev);
   w.plan_factor = VcCholPlan();
@@ -1475,7 +1477,7 @@ int vc_pick_reserved_sms(int num_sms, int rows_t /*row tiles below the panel*/, 
   }
   return best;
 }
-void vc_chol_factor(const VcMatrix& M, VcCholWork& w, int64_t* launches, int mode) {
+static void chol_factor_enqueue(const VcMatrix& M, VcCholWork& w, int64_t* launches, int mode) {
   const int nt = M.nt, nbt = M.nbt, nb = w.nb_tiles;
   // a K-panel of the trailing update must lie inside ONE storage block column (uniform leading dimension)
   if (nb != M.blk) throw VcError(VC_ERR_INVALID, "outer Cholesky block differs from the storage block of the matrix");
@@ -1563,6 +1565,61 @@ void vc_chol_factor(const VcMatrix& M, VcCholWork& w, int64_t* launches, int mod
   }
   VC_CUDA_TRY(cudaStreamWaitEvent(sm, w.ev_panel, 0));
   trace_dump(nt, nb);
+}
+
+// CUDA graph of one factorisation (small problems only).  At n <= 8 192 a factorisation is a chain of 40-600
+// short launches on two streams; replaying the captured graph takes the per-launch CPU cost and most of the
+// inter-kernel gaps out of it.  Everything in the sequence is fixed for a given (matrix buffers, slot count):
+// kernel arguments are addresses and tile lists, the parameters of the evaluations live in device memory (the
+// build is outside the graph).  VC_GRAPH=0 disables; tracing disables.
+constexpr int GRAPH_NT_MAX = 64;
+void vc_chol_free_graphs(VcCholWork& w) {
+  for (auto& g : w.graphs) if (g.exec) cudaGraphExecDestroy((cudaGraphExec_t)g.exec);
+  w.graphs.clear();
+}
+void vc_chol_factor(const VcMatrix& M, VcCholWork& w, int64_t* launches, int mode) {
+  static const bool graphs_on = !(getenv("VC_GRAPH") && atoi(getenv("VC_GRAPH")) == 0);
+  const bool eligible = graphs_on && mode == VC_SWEEP_FACTOR && w.lookahead && !w.legacy_syrk && !tracer().on &&
+                        M.nt <= GRAPH_NT_MAX;
+  if (!eligible) {
+    chol_factor_enqueue(M, w, launches, mode);
+    return;
+  }
+  const int nbatch = std::max(M.nbatch, 1);
+  for (auto& g : w.graphs)
+    if (g.a == M.a && g.b == M.b && g.nbatch == nbatch && g.nt == M.nt && g.nbt == M.nbt) {
+      VC_CUDA_TRY(cudaGraphLaunch((cudaGraphExec_t)g.exec, w.st_main));
+      *launches += g.launches;
+      return;
+    }
+  // the tile lists are uploaded with a blocking copy: that must happen before the capture starts
+  build_plan(w.plan_factor, M.nt, M.nbt, w.nb_tiles, true, mode);
+  const int64_t l0 = *launches;
+  cudaGraph_t graph = nullptr;
+  VC_CUDA_TRY(cudaStreamBeginCapture(w.st_main, cudaStreamCaptureModeThreadLocal));
+  try {
+    chol_factor_enqueue(M, w, launches, mode);
+  } catch (...) {
+    cudaStreamEndCapture(w.st_main, &graph);
+    if (graph) cudaGraphDestroy(graph);
+    throw;
+  }
+  VC_CUDA_TRY(cudaStreamEndCapture(w.st_main, &graph));
+  cudaGraphExec_t exec = nullptr;
+  const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (ie != cudaSuccess) {                       // no graph to be had: run the sequence directly
+    (void)cudaGetLastError();
+    *launches = l0;
+    chol_factor_enqueue(M, w, launches, mode);
+    return;
+  }
+  if (w.graphs.size() >= 8) {                    // a handful of slot counts occur in practice; drop the oldest
+    cudaGraphExecDestroy((cudaGraphExec_t)w.graphs.front().exec);
+    w.graphs.erase(w.graphs.begin());
+  }
+  w.graphs.push_back(VcGraphEntry{M.a, M.b, nbatch, M.nt, M.nbt, (void*)exec, *launches - l0});
+  VC_CUDA_TRY(cudaGraphLaunch(exec, w.st_main));
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -181,6 +181,11 @@ struct VcCholPlan {       // tile lists of every update launch, precomputed per 
   int* tiles_dev = nullptr;          // packed (I | J << 16), L2-friendly super-block order
   int64_t tiles_cap = 0;
 };
+struct VcGraphEntry {     // an instantiated CUDA graph of one factorisation (vc_chol_factor)
+  const double* a; const double* b; int nbatch, nt, nbt;
+  void* exec;             // cudaGraphExec_t
+  int64_t launches;       // kernels it replays
+};
 struct VcCholWork {
   double* linv;          // per slot: nt x (128 x 128), the inverse of every diagonal factor tile
   double* logdet_part;   // per slot: nt partial sums of log L_jj
@@ -193,6 +198,7 @@ struct VcCholWork {
   cudaStream_t st_main, st_panel;
   cudaEvent_t ev_panel, ev_update, ev_col;
   VcCholPlan plan_factor, plan_solve;
+  std::vector<VcGraphEntry> graphs;
 };
 enum { VC_SWEEP_FACTOR = 0,   // potrf + TRSM + updates on every row tile (main + border)
        VC_SWEEP_SOLVE = 1,    // factor already resident: only the border rows are swept
@@ -200,6 +206,7 @@ enum { VC_SWEEP_FACTOR = 0,   // potrf + TRSM + updates on every row tile (main 
 void vc_chol_init();
 void vc_chol_factor(const VcMatrix& M, VcCholWork& w, int64_t* launches, int mode = VC_SWEEP_FACTOR);
 void vc_chol_free_plans(VcCholWork& w);
+void vc_chol_free_graphs(VcCholWork& w);   // must be called when the matrix buffers are reallocated
 void vc_chol_invert_diag_tiles(const VcMatrix& M, VcCholWork& w, int64_t* launches);
 // raw launchers (used by the distributed driver, vc_dist.cu)
 // host-side address of local tile (lI, lJ)
