@@ -624,6 +624,9 @@ def run_ours(args):
         "gpu_launches": launches_total,
         "roofline": roof, "roofline_build": roof_build,
         "phases_ms": {k: v / K for k, v in phase.items()},
+        # device time of one step from CUDA events recorded on the library's own stream around build / Cholesky /
+        # finalize (rank 0; `ms_per_step` is the wall clock of the synchronised region, max over ranks)
+        "ms_per_step_device": sum(phase.values()) / K,
         "n2ll_sample": vals[:2],
     }
     line.update(extra)
