@@ -201,6 +201,12 @@ VC_API int vc_create_dist(vc_handle** h, const vc_config* cfg, int64_t n, int32_
  * n^2 8 (1/pr + 1/pc) / 2 a row / column-communicator scheme would need */
 VC_API int vc_dist_traffic(vc_handle* h, double* rx_bytes, double* rowcol_bound_bytes);
 
+/* host-only description of the lower block-column storage of an n x n matrix (no GPU needed; unit tests and sizing):
+ * block column c starts `off[c]` doubles into the slot, has leading dimension ld[c] and stores the row tiles from r0[c]
+ * on.  Returns the number of block columns (arrays are filled up to cap); *doubles_out = doubles per evaluation slot. */
+VC_API int vc_layout_describe(int64_t n, int32_t nb_outer, int64_t* doubles_out, int64_t* off, int32_t* ld,
+                              int32_t* r0, int32_t cap);
+
 /* host-only plan of a batch of m evaluations under S evaluation slots (no GPU needed; unit tests): evaluations that
  * repeat theta share a slot, the last valid evaluation lands in slot 0 of the last group.  valid may be NULL.
  * Returns the number of distinct thetas; group_of / slot_of / rec_of (m each) are -1 for invalid evaluations. */

@@ -351,3 +351,40 @@ def test_batch_plan_shares_slots_between_repeated_thetas_and_puts_the_last_evalu
         # records: dense, grouped by group, in evaluation order inside a group
         order = sorted(np.nonzero(ok)[0], key=lambda e: (g[e], e))
         assert [int(r[e]) for e in order] == list(range(len(order)))
+
+
+def test_lower_block_column_storage_table():
+    """Lower block-column storage: every block column stores the row tiles from its own
+    diagonal block down, with its own leading dimension (an odd number of 128-double tiles).  The ranges must not
+    overlap, must hold every lower tile, and one evaluation slot must be about half the full square:
+    n = 50 000 -> 10.3 GB, n = 150 000 -> 91 GB (fits one B200)."""
+    import ctypes as C
+    from varycoef_b200 import _lib
+    L = _lib.lib()
+    for n, nb in [(1, 0), (127, 0), (1000, 0), (1000, 128), (5300, 384), (50000, 0), (150000, 0)]:
+        cap = 4096
+        off = (C.c_int64 * cap)()
+        ld = (C.c_int32 * cap)()
+        r0 = (C.c_int32 * cap)()
+        tot = C.c_int64()
+        nbc = L.vc_layout_describe(n, nb, C.byref(tot), off, ld, r0, cap)
+        n_pad = -(-n // 128) * 128
+        nt = n_pad // 128
+        blk = (nb or (1024 if n_pad >= 40000 else (256 if n_pad <= 4096 else 512))) // 128
+        assert nbc == -(-nt // blk)
+        end_prev = 0
+        for c in range(nbc):
+            assert r0[c] == c * blk and off[c] == end_prev          # packed back to back, starts at its diagonal block
+            rows = nt - r0[c]
+            assert ld[c] % 128 == 0 and (ld[c] // 128) % 2 == 1 and ld[c] // 128 >= rows
+            assert ld[c] // 128 <= rows + 1                          # at most one padding tile
+            ncols = min(blk, nt - c * blk)
+            end_prev = off[c] + ld[c] * ncols * 128
+        assert tot.value == end_prev
+        full = 8.0 * n_pad * (n_pad + 128)
+        if n >= 50000:
+            assert tot.value * 8 < 0.53 * full
+    L.vc_layout_describe(50000, 0, C.byref(tot), None, None, None, 0)
+    assert 10.0e9 < tot.value * 8 < 10.6e9
+    L.vc_layout_describe(150000, 0, C.byref(tot), None, None, None, 0)
+    assert 90e9 < tot.value * 8 < 92.5e9

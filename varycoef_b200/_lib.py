@@ -82,6 +82,8 @@ SIGNATURES = {
                                  C.c_int32, _dp, _dp, _dp, _dp, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                  C.c_char_p]),
     "vc_dist_traffic": (C.c_int, [C.c_void_p, _dp, _dp]),
+    "vc_layout_describe": (C.c_int, [C.c_int64, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
+                                     C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int32]),
     "vc_plan_batch": (C.c_int, [C.c_int32, C.c_int32, _dp, C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_int32),
                                 C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "vc_bc_owner": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),

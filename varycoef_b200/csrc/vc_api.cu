@@ -35,6 +35,10 @@ extern "C" int vc_config_default(vc_config* cfg) {
   return VC_OK;
 }
 
+// outer Cholesky block = storage block.  Measured with batches of 16 (the stencils optim evaluates) and single
+// evaluations (profiles/r02_batch_small_n.md): 256 up to n = 4 096, 512 up to 40 000, 1024 beyond
+static int auto_outer_block(int64_t n_pad) { return n_pad >= 40000 ? 1024 : (n_pad <= 4096 ? 256 : 512); }
+
 static void upload_padded(double* dst, const double* src, int64_t n, int64_t n_pad, int cols,
                           cudaStream_t st) {
   // column-major n x cols -> n_pad x cols (tail rows stay zero)
@@ -188,10 +192,7 @@ vc_handle* vc_alloc_common(const vc_config* cfg, int64_t n, int d, int p, int q,
       VC_CUDA_TRY(cudaGetDeviceProperties(&prop, h->device));
       h->cw.num_sms = prop.multiProcessorCount;
     }
-    // outer block = storage block.  Measured with batches of 16 (the stencils optim evaluates) and single
-    // evaluations (profiles/r02_batch_small_n.md): 256 up to n = 4096, 512 up to 40 000, 1024 beyond
-    const int nb_auto = np >= 40000 ? 1024 : (np <= 4096 ? 256 : 512);
-    h->cw.nb_tiles = (cfg->nb_outer > 0 ? cfg->nb_outer : nb_auto) / VC_TILE;
+    h->cw.nb_tiles = (cfg->nb_outer > 0 ? cfg->nb_outer : auto_outer_block(np)) / VC_TILE;
     h->cw.lookahead = !(cfg->flags & VC_FLAG_NO_LOOKAHEAD);
     h->cw.st_main = h->st_main; h->cw.st_panel = h->st_panel;
     if (alloc_matrix) {
@@ -383,6 +384,28 @@ int vc_make_theta(const vc_handle* h, const double* theta, VcTheta* t) {
   t->tau2 = theta[2 * h->q];
   if (!isfinite(t->tau2)) return VC_ERR_INVALID;
   return VC_OK;
+}
+
+// Test hook (host only): the lower block-column storage table of a single-GPU matrix of order n with outer block
+// nb_outer (0 = the automatic choice): per block column its offset (doubles), leading dimension and first stored
+// row tile.  Returns the number of block columns; *doubles_out = size of one evaluation slot.
+extern "C" int vc_layout_describe(int64_t n, int32_t nb_outer, int64_t* doubles_out, int64_t* off, int32_t* ld,
+                                  int32_t* r0, int32_t cap) {
+  if (n < 1 || nb_outer < 0 || nb_outer % VC_TILE != 0) return -1;
+  const int64_t np = (n + VC_TILE - 1) / VC_TILE * VC_TILE;
+  const int nt = (int)(np / VC_TILE);
+  const int blk = (nb_outer > 0 ? nb_outer : auto_outer_block(np)) / VC_TILE;
+  std::vector<int> r0v, ncols;
+  for (int c = 0; c * blk < nt; ++c) { r0v.push_back(c * blk); ncols.push_back(std::min(blk, nt - c * blk)); }
+  std::vector<VcColBlock> cb;
+  const int64_t total = vc_layout_fill(cb, r0v, ncols, nt);
+  if (doubles_out) *doubles_out = total;
+  for (int c = 0; c < (int)cb.size() && c < cap; ++c) {
+    if (off) off[c] = cb[c].off;
+    if (ld) ld[c] = cb[c].ld;
+    if (r0) r0[c] = cb[c].r0;
+  }
+  return (int)cb.size();
 }
 
 // ---- host-side plan of a batch (no CUDA: unit-tested on the CPU through vc_plan_batch) ----------------------
