@@ -291,6 +291,7 @@ extern "C" int vc_create_dist(vc_handle** out, const vc_config* cfg_in, int64_t 
   if (!locs || !X || !W || !y || !nccl_id) return vc_fail(nullptr, VC_ERR_INVALID, "NULL input pointer");
   if (pr < 1 || pc < 1 || pr * pc != world || rank < 0 || rank >= world)
     return vc_fail(nullptr, VC_ERR_INVALID, "process grid pr x pc must equal the world size");
+  if (pr > 8) return vc_fail(nullptr, VC_ERR_INVALID, "at most 8 process rows (VcPanelMap)");
   std::string why;
   if (vc_validate_cfg(&cfg, n, d, p, q, why) != VC_OK) return vc_fail(nullptr, VC_ERR_INVALID, why);
   if (!g_nccl.load()) return vc_fail(nullptr, VC_ERR_CUDA, g_nccl.err);
