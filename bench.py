@@ -324,11 +324,10 @@ def run_reference(args):
     build_full = tb_l * (n / n_l) ** 2            # the O(n^2) numpy passes of the faithful Sigma_y loop
     full = None
     if not args.no_lean_full:
-        try:
-            full = full_size_cpu(n, p, cov, seed_off, threads, with_dgesv=True)
-            log("reference: measured at full n:", json.dumps(full)[:400])
-        except Exception as e:  # noqa: BLE001
-            full = {"skipped": "failed: %r" % (e,)}
+        full = run_child("cpu_full", args)          # 40 GB, 16 BLAS threads: isolated from this process
+        if "failed" in full:
+            full = {"skipped": full["failed"]}
+        log("reference: measured at full n:", json.dumps(full)[:400])
     if full and "dgesv_s" in full:
         # cubic part of the faithful sequence MEASURED at the full n: dpotrf + 3 x dgesv(t(R), .) (one of the three
         # identical factorisations timed); only the O(n^2) build is scaled from the largest faithful sample
@@ -362,6 +361,65 @@ def run_reference(args):
             "e2e": {"value": arm["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "wall_s": wall}
     emit(line)
+
+
+# ------------------------------------------------------------------------------------------------
+# Records outside the timed region run in CHILD processes: they use other native stacks (cuSOLVER / cuBLAS through
+# torch, OpenBLAS on 16 threads) on 20-60 GB, and a native fault in one of them must not take the headline line
+# with it (one driver-like run of round 2 died with SIGSEGV after the timed legs; it did not reproduce).
+# ------------------------------------------------------------------------------------------------
+def run_child(kind, args, device=0, timeout=1500):
+    cmd = [sys.executable, os.path.abspath(__file__), "--child", kind, "--workload", args.workload, "--device", str(device)]
+    if args.n:
+        cmd += ["--problem-n", str(args.n)]
+    env = dict(os.environ)
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT"):
+        env.pop(k, None)
+    try:
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=timeout, env=env)
+    except subprocess.TimeoutExpired:
+        return {"failed": "child %s timed out after %d s" % (kind, timeout)}
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip().startswith("{")]
+    if r.returncode != 0 or not lines:
+        return {"failed": "child %s exited with code %d" % (kind, r.returncode), "stderr_tail": r.stderr[-400:]}
+    try:
+        return json.loads(lines[-1])
+    except Exception as e:  # noqa: BLE001
+        return {"failed": "child %s printed no JSON: %r" % (kind, e)}
+
+
+def child_main(args):
+    """`bench.py --child KIND`: one record, printed as one JSON object on stdout."""
+    n, p, cov, taper, seed_off, desc = WORKLOADS[args.workload]
+    if args.n:
+        n = args.n
+    if args.child == "cpu_baseline":            # numpy / OpenBLAS only: torch is never imported here
+        emit(cpu_baseline_gpu_arm(n, p, cov, seed_off, blas_threads()))
+        return
+    if args.child == "cpu_full":                # reference arm: lean sequence + one dgesv at the full n
+        emit(full_size_cpu(n, p, cov, seed_off, blas_threads(), with_dgesv=True))
+        return
+    import torch
+    from varycoef_b200 import SVCObjective
+    torch.cuda.set_device(args.device)
+    out = {}
+    locs, X, y, L = make_inputs(n, p, seed_off)
+    theta = theta_stencil(n, p, p, L, y)[0]
+    if args.child in ("parity", "parity_library"):
+        try:
+            with SVCObjective(y, X, locs, cov_name=cov, tapering=taper, profileLik=True, device=args.device) as obj:
+                out["parity"] = parity_record(obj, theta, X, y, args.device)
+        except Exception as e:  # noqa: BLE001
+            out["parity"] = {"failed": repr(e)}
+        torch.cuda.empty_cache()
+    if args.child in ("library_bar", "parity_library"):
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            from third_path import library_bar
+            out["library_bar"] = library_bar(n, args.device)
+        except Exception as e:  # noqa: BLE001
+            out["library_bar"] = {"failed": repr(e)}
+    emit(out)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -546,12 +604,6 @@ def run_ours(args):
     # ---- records outside the timed region ----
     extra = {}
     at_size = (n == WORKLOADS[args.workload][0])
-    if world == 1 and not args.no_parity:
-        try:
-            extra["parity"] = parity_record(obj, thetas[0], X, y, local)
-        except Exception as e:  # noqa: BLE001
-            extra["parity"] = {"failed": repr(e)}
-        torch.cuda.empty_cache()
     single_c3 = None
     if world > 1 and not args.no_sharded and args.workload == "c3" and at_size:
         r0 = obj.n2LL(thetas[0], parts=True)
@@ -560,14 +612,13 @@ def run_ours(args):
     obj.close()
     del obj
     torch.cuda.empty_cache()
-    if world == 1 and not args.no_library_bar:
-        try:
-            sys.path.insert(0, os.path.join(ROOT, "tools"))
-            from third_path import library_bar
-            extra["library_bar"] = library_bar(n, local)
-        except Exception as e:  # noqa: BLE001
-            extra["library_bar"] = {"failed": repr(e)}
-        torch.cuda.empty_cache()
+    if world == 1 and not (args.no_parity and args.no_library_bar):
+        kind = "parity_library" if not (args.no_parity or args.no_library_bar) else ("parity" if args.no_library_bar else "library_bar")
+        rec = run_child(kind, args, device=local)
+        if "failed" in rec:
+            extra["parity" if kind != "library_bar" else "library_bar"] = rec
+        else:
+            extra.update(rec)
     if single_c3 is not None:
         try:
             extra["sharded"] = sharded_record(args, dist, world, rank, local, peak_tf.value, single_c3)
@@ -631,7 +682,9 @@ def run_ours(args):
     }
     line.update(extra)
     if world == 1 and not args.no_cpu:
-        line["cpu_baseline"] = cpu_baseline_gpu_arm(n, p, cov, seed_off, blas_threads())
+        line["cpu_baseline"] = run_child("cpu_baseline", args)
+        if "failed" in line["cpu_baseline"]:
+            line["cpu_baseline"].update({"value": None, "unit": UNIT, "cores": _host_threads(), "kind": "port", "sample": "child process failed"})
     emit(line)
     if dist is not None:
         dist.destroy_process_group()
@@ -740,9 +793,13 @@ def main():
     ap.add_argument("--sharded-n", type=int, default=0, help="override n of the sharded record (debug)")
     ap.add_argument("--sharded-steps", type=int, default=2)
     ap.add_argument("--nb", type=int, default=0, help="outer Cholesky block (0 = auto)")
+    ap.add_argument("--child", default="", help=argparse.SUPPRESS)     # internal: one record in a child process
+    ap.add_argument("--device", type=int, default=0, help=argparse.SUPPRESS)
     ap.add_argument("--force-dist", action="store_true", help="--workload c4 at N = 1: use the block-cyclic driver on a 1x1 grid")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.child:
+        child_main(args)
+    elif args.impl == "reference":
         run_reference(args)
     elif args.workload == "c4":
         run_dist(args)
