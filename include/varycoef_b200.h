@@ -197,6 +197,11 @@ VC_API int vc_create_dist(vc_handle** h, const vc_config* cfg, int64_t n, int32_
                    const double* locs, const double* X, const double* W, const double* y,
                    int32_t rank, int32_t world, int32_t pr, int32_t pc, const char nccl_id[128]);
 
+/* host-only: order of the row tiles >= oe in the gathered panel buffer of the sharded path (owner-major: process row 0,
+ * its border tiles, process row 1, ...): first position / tile count per process row, position of every row tile
+ * oe .. nt + nbt - 1.  Every process row's part is one contiguous range = one broadcast.  Returns the tile count. */
+VC_API int vc_bc_panel_layout(int32_t nt, int32_t nbt, int32_t nb, int32_t pr, int32_t oe, int32_t* chunk_off,
+                              int32_t* chunk_cnt, int32_t* pos);
 /* NVLink bytes this rank receives per evaluation (panel + L_DD broadcasts on the world communicator), next to the
  * n^2 8 (1/pr + 1/pc) / 2 a row / column-communicator scheme would need */
 VC_API int vc_dist_traffic(vc_handle* h, double* rx_bytes, double* rowcol_bound_bytes);

@@ -27,7 +27,7 @@ def _init(rank, world, port):
 
 
 def _bc_cholesky_worker(rank, world, port, pr, pc, nt, nb, T, q_out):
-    import ctypes as C
+    import ctypes as C  # noqa: N812
     from varycoef_b200 import _lib
     L = _lib.lib()
     _init(rank, world, port)
@@ -71,18 +71,27 @@ def _bc_cholesky_worker(rank, world, port, pr, pc, nt, nb, T, q_out):
                         loc[(I, J)] = row[:, k * T:(k + 1) * T].copy()
         if oe >= nt:
             continue
-        # 3. every distribution block of the panel is broadcast by its owner
-        panel = {}
-        for B in range(oe // nb, nblocks):
-            t0, t1 = B * nb, min(B * nb + nb, nt)
-            root = (B % pr) * pc + pcp
-            buf = torch.zeros(((t1 - t0) * T, K), dtype=torch.float64)
-            if rank == root:
-                buf = torch.from_numpy(np.vstack([np.hstack([loc[(I, J)] for J in range(ob, oe)])
-                                                  for I in range(t0, t1)]))
-            dist.broadcast(buf, src=root)
-            for k, I in enumerate(range(t0, t1)):
-                panel[I] = buf.numpy()[k * T:(k + 1) * T]
+        # 3. the gathered panel buffer is OWNER-major (vc_bc_panel_layout): every process row's part is one contiguous
+        #    range and travels in ONE broadcast from its owner in the panel's process column (round 2; round 1 sent
+        #    one broadcast per distribution block)
+        ntl = nt - oe
+        off = (C.c_int32 * 8)()
+        cnt = (C.c_int32 * 8)()
+        pos = (C.c_int32 * ntl)()
+        assert L.vc_bc_panel_layout(nt, 0, nb, pr, oe, off, cnt, pos) == ntl
+        buf = torch.zeros((ntl * T, K), dtype=torch.float64)
+        for I in range(oe, nt):                                   # pack: this rank's rows of the panel at their positions
+            if my_pc == pcp and (I // nb) % pr == my_pr:
+                q = pos[I - oe]
+                buf[q * T:(q + 1) * T] = torch.from_numpy(np.hstack([loc[(I, J)] for J in range(ob, oe)]))
+        nbcast = 0
+        for r in range(pr):
+            if cnt[r] > 0:
+                chunk = buf[off[r] * T:(off[r] + cnt[r]) * T]     # a view: received in place, like the NCCL broadcast
+                dist.broadcast(chunk, src=r * pc + pcp)
+                nbcast += 1
+        assert nbcast <= pr
+        panel = {I: buf.numpy()[pos[I - oe] * T:(pos[I - oe] + 1) * T] for I in range(oe, nt)}
         # 4. trailing update of the tiles the C library assigns to this rank
         cnt = L.vc_bc_trailing_tiles(nt, 0, nb, pr, pc, rank, oe, None, 0)
         out = (C.c_int32 * max(cnt, 1))()

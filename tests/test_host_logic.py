@@ -256,10 +256,15 @@ def test_plain_c_client_links_and_validates_arguments(tmp_path):
 
 def test_owner_major_panel_map_is_a_bijection_with_contiguous_owner_ranges():
     """Sharded path: the gathered panel buffer holds the row tiles >= oe in OWNER-major order (VcPanelMap,
-    csrc/vc_common.cuh) so that every process row's part is ONE contiguous range = one NCCL broadcast.  The device
-    function vc_panel_pos is compiled for the host here and checked for every step of a few grids: positions are a
-    bijection onto 0 .. count-1, every owner's tiles are contiguous and in tile order, border tiles follow process
-    row 0's main tiles."""
+    csrc/vc_common.cuh; filled by fill_panel_map in csrc/vc_dist.cu) so that every process row's part is ONE
+    contiguous range = one NCCL broadcast.  vc_bc_panel_layout exposes the map the plan uses; the device function
+    vc_panel_pos is additionally compiled for the host from the header.  For every step of a few grids: positions
+    are a bijection onto 0 .. count-1, every owner's tiles are contiguous and in tile order, border tiles follow
+    process row 0's main tiles, and header and library agree."""
+    import ctypes as C
+    import tempfile
+    from varycoef_b200 import _lib
+    L = _lib.lib()
     src = r"""
 #include <stdio.h>
 #include <string.h>
@@ -271,7 +276,7 @@ int main(int argc, char** argv) {
     m.pr = pr; m.nb = nb; m.nt = nt;
     const int nblocks = (nt + nb - 1) / nb, B0 = (oe + nb - 1) / nb;
     int pos = 0;
-    for (int r = 0; r < pr; ++r) {                        // as build_dist_plan (csrc/vc_dist.cu) fills it
+    for (int r = 0; r < pr; ++r) {                        // an independent restatement of the rule
       int bf = B0; while (bf % pr != r) ++bf;
       m.bfirst[r] = bf; m.chunk_off[r] = pos;
       int cnt = 0;
@@ -285,7 +290,6 @@ int main(int argc, char** argv) {
   return 0;
 }
 """
-    import tempfile
     cases = []
     for nt, nb, pr, nbt in [(40, 4, 2, 1), (41, 4, 4, 1), (37, 8, 4, 2), (16, 2, 1, 1), (1172, 8, 4, 1)]:
         for oe in range(nb, nt, nb * (1 if nt < 100 else 37)):
@@ -302,14 +306,19 @@ int main(int argc, char** argv) {
     for (nt, nb, pr, nbt, oe), line in zip(cases, out):
         pos = [int(v) for v in line.split()]
         tiles = list(range(oe, nt + nbt))
+        off = (C.c_int32 * 8)()
+        cnt = (C.c_int32 * 8)()
+        lp = (C.c_int32 * len(tiles))()
+        assert L.vc_bc_panel_layout(nt, nbt, nb, pr, oe, off, cnt, lp) == len(tiles)
+        assert list(lp) == pos                                                        # library == header restatement
         assert sorted(pos) == list(range(len(tiles))), (nt, nb, pr, oe)
         owner = [((I // nb) % pr) if I < nt else 0 for I in tiles]
         for r in range(pr):
-            mine = [(q, I) for q, I, o in zip(pos, tiles, owner) if o == r]
-            if mine:
-                qs = [q for q, _ in mine]
-                assert qs == list(range(min(qs), min(qs) + len(qs))), (nt, nb, pr, oe, r)     # contiguous, in tile order
-        # plain order when pr == 0 is covered by the device tests of the 1 x 1 grid
+            qs = [q for q, o in zip(pos, owner) if o == r]
+            assert len(qs) == cnt[r]
+            if qs:
+                assert qs == list(range(off[r], off[r] + cnt[r])), (nt, nb, pr, oe, r)  # contiguous, in tile order
+    assert L.vc_bc_panel_layout(10, 1, 4, 9, 4, None, None, None) == -1
 
 
 def test_batch_plan_shares_slots_between_repeated_thetas_and_puts_the_last_evaluation_in_slot_0():

@@ -89,6 +89,7 @@ SIGNATURES = {
     "vc_bc_owner": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "vc_bc_local": (C.c_int, [C.c_int32, C.c_int32]),
     "vc_bc_count": (C.c_int, [C.c_int32, C.c_int32, C.c_int32]),
+    "vc_bc_panel_layout": (C.c_int, [C.c_int32] * 5 + [C.POINTER(C.c_int32)] * 3),
     "vc_bc_trailing_tiles": (C.c_int, [C.c_int32] * 7 + [C.POINTER(C.c_int32), C.c_int32]),
 }
 

@@ -60,6 +60,44 @@ extern "C" int vc_bc_trailing_tiles(int32_t nt, int32_t nbt, int32_t nb, int32_t
   return (int)v.size();
 }
 
+// Owner-major order of the row tiles >= oe in a gathered panel buffer (VcPanelMap, vc_common.cuh): the tiles of process
+// row 0 (then the border tiles, which belong to it), then process row 1, ...  cnt[r] = tiles of process row r.
+static void fill_panel_map(VcPanelMap& m, int cnt[8], int nt, int nbt, int nb, int pr, int oe) {
+  memset(&m, 0, sizeof(m));
+  m.pr = pr; m.nb = nb; m.nt = nt;
+  const int nblocks = (nt + nb - 1) / nb;
+  const int B0 = (oe + nb - 1) / nb;                   // first distribution block in the buffer (oe is block-aligned)
+  int pos = 0;
+  for (int r = 0; r < pr; ++r) {
+    int bf = B0;
+    while (bf % pr != r) ++bf;
+    m.bfirst[r] = bf;
+    m.chunk_off[r] = pos;
+    int c = 0;
+    for (int B = bf; B < nblocks; B += pr) c += std::min(nb, nt - B * nb);
+    if (r == 0) { m.main0 = c; c += nbt; }
+    cnt[r] = c;
+    pos += c;
+  }
+}
+// host-only view of that order (unit tests): per process row its first position and tile count, per row tile
+// I = oe .. nt + nbt - 1 its position in the buffer.  Returns the number of tiles in the buffer.
+extern "C" int vc_bc_panel_layout(int32_t nt, int32_t nbt, int32_t nb, int32_t pr, int32_t oe, int32_t* chunk_off,
+                                  int32_t* chunk_cnt, int32_t* pos) {
+  if (nt < 1 || nbt < 0 || nb < 1 || pr < 1 || pr > 8 || oe < 0 || oe > nt) return -1;
+  VcPanelMap m;
+  int cnt[8];
+  fill_panel_map(m, cnt, nt, nbt, nb, pr, oe);
+  int total = 0;
+  for (int r = 0; r < pr; ++r) {
+    if (chunk_off) chunk_off[r] = m.chunk_off[r];
+    if (chunk_cnt) chunk_cnt[r] = cnt[r];
+    total += cnt[r];
+  }
+  if (pos) for (int I = oe; I < nt + nbt; ++I) pos[I - oe] = vc_panel_pos(m, I, oe);
+  return total;
+}
+
 // ---- NCCL through dlopen (the library already loaded by the host process is reused) ----------
 typedef struct ncclComm* ncclComm_t;
 typedef struct { char internal[128]; } ncclUniqueId;
@@ -230,28 +268,16 @@ static void build_dist_plan(vc_handle* h, VcDist* D) {
     // the gathered panel buffer holds the row tiles >= oe in OWNER-major order (VcPanelMap); every process row's
     // part is contiguous and is broadcast by its owner in the panel's process column in one operation
     {
-      VcPanelMap& m = st.map;
-      memset(&m, 0, sizeof(m));
-      m.pr = pr; m.nb = nb; m.nt = nt;
-      const int B0 = (st.oe + nb - 1) / nb;            // first distribution block in the buffer (oe is block-aligned)
-      int pos = 0;
-      for (int r = 0; r < pr; ++r) {
-        int bf = B0;
-        while (bf % pr != r) ++bf;
-        m.bfirst[r] = bf;
-        m.chunk_off[r] = pos;
-        int cnt = 0;
-        for (int B = bf; B < nblocks; B += pr) cnt += std::min(nb, nt - B * nb);
-        if (r == 0) { m.main0 = cnt; cnt += nbt; }     // border tiles belong to process row 0
-        if (st.oe < nt && cnt > 0) {
+      int cnt[8];
+      fill_panel_map(st.map, cnt, nt, nbt, nb, pr, st.oe);
+      for (int r = 0; r < pr; ++r)
+        if (st.oe < nt && cnt[r] > 0) {
           BcastOp op;
-          op.off = (int64_t)pos * VC_TILE * Kb;
-          op.count = (int64_t)cnt * VC_TILE * Kb;
+          op.off = (int64_t)st.map.chunk_off[r] * VC_TILE * Kb;
+          op.count = (int64_t)cnt[r] * VC_TILE * Kb;
           op.root = r * pc + st.pcp;
           st.bcasts.push_back(op);
         }
-        pos += cnt;
-      }
     }
     {
       std::vector<int> tr;
