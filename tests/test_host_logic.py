@@ -397,3 +397,31 @@ def test_lower_block_column_storage_table():
     assert 10.0e9 < tot.value * 8 < 10.6e9
     L.vc_layout_describe(150000, 0, C.byref(tot), None, None, None, 0)
     assert 90e9 < tot.value * 8 < 92.5e9
+
+
+def test_bench_child_records_fail_soft():
+    """bench.py runs parity / library_bar / cpu_baseline in child processes so that a native fault there cannot take
+    the headline JSON line with it.  In this GPU-less container the GPU child dies (no driver): the parent must get a
+    {"failed": ...} record, not an exception; the CPU child must deliver a measured record."""
+    code = r"""
+import argparse, json, sys
+sys.argv = ["bench.py"]
+import bench
+a = argparse.Namespace(workload="c3", n=1500)
+gpu = bench.run_child("parity_library", a, device=0, timeout=300)
+cpu = bench.run_child("cpu_baseline", a, timeout=300)
+bench.emit({"gpu": gpu, "cpu": cpu})
+"""
+    out = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-800:]
+    import json
+    d = json.loads([ln for ln in out.stdout.splitlines() if ln.startswith("{")][-1])
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if not has_gpu:
+        assert "failed" in d["gpu"] and "exited with code" in d["gpu"]["failed"]
+    assert d["cpu"]["kind"] == "port" and d["cpu"]["value"] > 0 and d["cpu"]["extrapolated"] is False
+    assert d["cpu"]["detail"]["n"] == 1500
