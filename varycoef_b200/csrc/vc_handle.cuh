@@ -8,7 +8,7 @@ struct vc_handle {
   int d = 0, p = 0, q = 0;
   int device = 0;
   VcMatrix M{};
-  std::vector<VcColBlock> cb_host;   // block-column storage table of M (and of every lane); device copy in cb_dev
+  std::vector<VcColBlock> cb_host;   // block-column storage table of M (one table for all evaluation slots); device copy in cb_dev
   VcColBlock* cb_dev = nullptr;
   // O(n) inputs, zero-padded to n_pad, column-major
   double *locs = nullptr, *x = nullptr, *w = nullptr, *y = nullptr;
