@@ -16,10 +16,10 @@ which points the objective is evaluated at:
 The L-BFGS-B iteration itself is scipy's (Fortran L-BFGS-B 3.0; R ships the 2.x C translation),
 so iteration counts can differ slightly from R while optima agree.
 
-What is B200-specific: all probes of one gradient (2 npar points) or of the whole Hessian
-stencil go to the objective in ONE batch call (`fn_batch`), which the GPU library queues back to
-back with a single synchronisation -- the role optimParallel plays in the reference
-(R-pkg/R/SVC_mle.R:164-200).
+What is B200-specific: the value at a point and all probes of its gradient (1 + 2 npar points), or the
+whole Hessian stencil, go to the objective in ONE batch call (`fn_batch`), which the GPU library sweeps
+with a single launch sequence (evaluation slots, shared factorisations for repeated thetas) -- the role
+optimParallel plays in the reference (R-pkg/R/SVC_mle.R:164-200).
 """
 from __future__ import annotations
 
@@ -118,19 +118,32 @@ def optim_lbfgsb(par, fn=None, fn_batch=None, lower=None, upper=None, hessian=Fa
     fb = _as_batch(fn, fn_batch)
     counts = {"fn": 0, "gr": 0, "evals": 0}
 
+    # L-BFGS-B asks for the value and the gradient at EVERY point it visits (R's lbfgsb.c calls fn then gr; scipy's
+    # driver calls fun_and_grad), and the numeric gradient is a stencil of 2 npar more evaluations around that point.
+    # On a GPU one batch of 1 + 2 npar evaluations costs little more than a single evaluation (vc_n2ll_batch sweeps
+    # them with one launch sequence), so the value call evaluates the stencil along with it and the gradient call
+    # that follows at the same point is served from that batch.  Counts keep R's meaning (optimiser-level calls).
+    memo = {"x": None, "vals": None, "div": None}
+
     def f_scaled(xs):
         counts["fn"] += 1
-        counts["evals"] += 1
-        v = float(np.asarray(fb((xs * parscale)[None, :]))[0]) / fnscale
+        pts, div = fd_points(xs, parscale, ndeps, lower_s, upper_s)
+        vals = np.asarray(fb(np.vstack([(xs * parscale)[None, :], pts])), dtype=np.float64) / fnscale
+        counts["evals"] += vals.size
+        v = float(vals[0])
         if not np.isfinite(v):
             raise FloatingPointError("L-BFGS-B needs finite values of 'fn'")
+        memo["x"], memo["vals"], memo["div"] = np.array(xs, copy=True), vals[1:], div
         return v
 
     def g_scaled(xs):
         counts["gr"] += 1
-        pts, div = fd_points(xs, parscale, ndeps, lower_s, upper_s)
-        vals = np.asarray(fb(pts), dtype=np.float64) / fnscale
-        counts["evals"] += vals.size
+        if memo["x"] is not None and np.array_equal(memo["x"], xs):
+            vals, div = memo["vals"], memo["div"]
+        else:
+            pts, div = fd_points(xs, parscale, ndeps, lower_s, upper_s)
+            vals = np.asarray(fb(pts), dtype=np.float64) / fnscale
+            counts["evals"] += vals.size
         if not np.all(np.isfinite(vals)):
             raise FloatingPointError("L-BFGS-B needs finite values of 'fn'")
         return (vals[0::2] - vals[1::2]) / div
